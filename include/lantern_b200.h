@@ -1,0 +1,228 @@
+/*
+ * lantern_b200 -- C ABI of the B200-native HNSW search/build engine.
+ *
+ * This is the drop-in boundary ("B1"): the entry points Lantern's access method
+ * (lantern_hnsw/src/hnsw/{scan,build}.c) and lantern_cli's external indexer bind today through the
+ * usearch C API (/root/reference/lantern_hnsw/third_party/usearch/c/usearch.h, "U/c/usearch.h"
+ * below), re-exported here with identical argument meaning and error behaviour, plus the batch
+ * entry points the reference lacks (it searches one query per call, scan.c:64,220-228).
+ *
+ * Conventions (all inherited from U/c/usearch.h):
+ *   - every call takes `lb200_error_t* error`; on failure the callee stores a pointer to a static,
+ *     never-freed C string and returns 0 / NULL (usearch.h:35-39; lib.cpp:183-189 pattern);
+ *   - handles are owned by the caller and released with lb200_free (usearch.h:146);
+ *   - vectors are copied on add (lib.cpp:89 force_vector_copy=true); result buffers are caller-owned;
+ *   - keys are opaque u64 (Lantern: 6-byte heap TID; 0 = deleted, hnsw.h:40); UINT64_MAX is the
+ *     reserved "free" key (index_dense.hpp:438) and is rejected by lb200_add*;
+ *   - hamming dimensions are given in BITS (scan.c:84-88);
+ *   - expansion = max(ef, k) (index.hpp:2706); ef == 0 means "index default" (usearch.h:265-271).
+ *     Unlike the vendored shim (lib.cpp:394 drops ef) a non-zero ef IS honoured.
+ *
+ * Every symbol is also exported under its reference name (`usearch_*`, same signature) so that
+ * lantern.so can link this library in place of U/c/lib.cpp; see INTEGRATION.md.
+ *
+ * There is no CPU fallback: every compute entry point fails with "CUDA device unavailable" when no
+ * sm_100 GPU is present.
+ */
+#ifndef LANTERN_B200_H
+#define LANTERN_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LB200_EXPORT __attribute__((visibility("default")))
+
+typedef void* lb200_index_t;       /* U/c/usearch.h:20 usearch_index_t */
+typedef uint64_t lb200_key_t;      /* :21 usearch_key_t */
+typedef float lb200_distance_t;    /* :25 usearch_distance_t */
+typedef char const* lb200_error_t; /* :39 usearch_error_t */
+typedef void* (*lb200_node_retriever_t)(void* ctx, unsigned long long index); /* :29 */
+typedef lb200_distance_t (*lb200_metric_t)(void const*, void const*);         /* :45 */
+
+/* U/c/usearch.h:51-63 -- numeric values are part of the ABI */
+typedef enum lb200_metric_kind_t {
+    lb200_metric_unknown_k = 0,
+    lb200_metric_cos_k = 1,
+    lb200_metric_ip_k = 2,
+    lb200_metric_l2sq_k = 3,
+    lb200_metric_haversine_k = 4,
+    lb200_metric_divergence_k = 5,
+    lb200_metric_pearson_k = 6,
+    lb200_metric_jaccard_k = 7,
+    lb200_metric_hamming_k = 8,
+    lb200_metric_tanimoto_k = 9,
+    lb200_metric_sorensen_k = 10,
+} lb200_metric_kind_t;
+
+/* U/c/usearch.h:65-72 */
+typedef enum lb200_scalar_kind_t {
+    lb200_scalar_unknown_k = 0,
+    lb200_scalar_f32_k = 1,
+    lb200_scalar_f64_k = 2,
+    lb200_scalar_f16_k = 3,
+    lb200_scalar_i8_k = 4,
+    lb200_scalar_b1_k = 5,
+} lb200_scalar_kind_t;
+
+/* U/c/usearch.h:74-117 -- field-for-field identical layout to usearch_init_options_t */
+typedef struct lb200_init_options_t {
+    lb200_metric_kind_t metric_kind;
+    lb200_metric_t metric; /* custom metrics are not supported on the GPU: must be NULL */
+    lb200_scalar_kind_t quantization;
+    size_t dimensions;
+    size_t connectivity;     /* M; 0 -> 16 */
+    size_t expansion_add;    /* ef_construction; 0 -> 128 */
+    size_t expansion_search; /* ef; 0 -> 64 */
+    bool multi;              /* must be false (Lantern never sets it) */
+    void* retriever_ctx;     /* external (Postgres-page) node retrievers have no meaning for HBM-resident */
+    lb200_node_retriever_t retriever;     /* graphs: must be NULL; use lb200_load_buffer on the index file */
+    lb200_node_retriever_t retriever_mut;
+    size_t num_threads; /* ignored: parallelism is the GPU's */
+    bool pq;
+    size_t num_centroids;
+    size_t num_subvectors;
+} lb200_init_options_t;
+
+/* U/c/usearch.h:119-131 */
+typedef struct lb200_index_metadata_t {
+    lb200_init_options_t init_options;
+    double inverse_log_connectivity;
+    size_t neighbors_bytes;      /* 4 + 6*M   (file-format width, index.hpp:1838) */
+    size_t neighbors_base_bytes; /* 4 + 12*M */
+    size_t dimensions;
+    size_t expansion_search;
+    size_t expansion_add;
+    size_t connectivity;
+    lb200_metric_kind_t metric_kind;
+} lb200_index_metadata_t;
+
+/* Work counters of the most recent search batch -- the reference's own definition of work
+ * (index.hpp:2370-2374, 2697-2727), used for the roofline's algorithmic bytes. */
+typedef struct lb200_search_stats_t {
+    uint64_t queries;
+    uint64_t computed_distances; /* == usearch search_result_t::computed_distances summed over the batch */
+    uint64_t base_pops;          /* level-0 candidates expanded */
+    uint64_t upper_hops;         /* level>=1 neighbour lists scanned */
+    uint64_t algorithmic_bytes;  /* computed_distances*row_bytes + (base_pops*(4+4*M0) + upper_hops*(4+4*M)) + queries*row_bytes */
+} lb200_search_stats_t;
+
+/* ---- lifecycle: U/c/usearch.h:140-146, lib.cpp:130-176 ---------------------------------------- */
+/* `codebook` (float[num_centroids][dimensions]) is copied to the device (the reference borrows it). */
+LB200_EXPORT lb200_index_t lb200_init(lb200_init_options_t* options, float* codebook, lb200_error_t* error);
+LB200_EXPORT void lb200_free(lb200_index_t, lb200_error_t* error);
+
+/* ---- introspection: usearch.h:224-229, 191 ---------------------------------------------------- */
+LB200_EXPORT size_t lb200_size(lb200_index_t, lb200_error_t* error);
+LB200_EXPORT size_t lb200_capacity(lb200_index_t, lb200_error_t* error);
+LB200_EXPORT size_t lb200_dimensions(lb200_index_t, lb200_error_t* error);
+LB200_EXPORT size_t lb200_connectivity(lb200_index_t, lb200_error_t* error);
+LB200_EXPORT size_t lb200_expansion_add(lb200_index_t, lb200_error_t* error);
+LB200_EXPORT size_t lb200_expansion_search(lb200_index_t, lb200_error_t* error);
+LB200_EXPORT lb200_index_metadata_t lb200_index_metadata(lb200_index_t, lb200_error_t* error);
+
+/* ---- build path: usearch.h:236-247; batch forms are new ---------------------------------------- */
+LB200_EXPORT void lb200_reserve(lb200_index_t, size_t capacity, lb200_error_t* error);
+/* Stages one vector (host memory, `vector_kind` f32 or b1 as Lantern passes them, build.c:128);
+ * the graph is extended on the GPU at the next lb200_build / search / save. */
+LB200_EXPORT void lb200_add(lb200_index_t, lb200_key_t key, void const* vector, lb200_scalar_kind_t vector_kind,
+                            lb200_error_t* error);
+/* n vectors, `stride` bytes apart, host memory. */
+LB200_EXPORT void lb200_add_batch(lb200_index_t, lb200_key_t const* keys, void const* vectors, size_t n, size_t stride,
+                                  lb200_scalar_kind_t vector_kind, lb200_error_t* error);
+/* Same, vectors already resident in device memory (f32 rows, or packed bits for b1). */
+LB200_EXPORT void lb200_add_batch_device(lb200_index_t, lb200_key_t const* host_keys, void const* device_vectors,
+                                         size_t n, size_t stride, lb200_scalar_kind_t vector_kind, lb200_error_t* error);
+/* Inserts every staged vector into the HNSW graph on the GPU (index.hpp:2479-2564 semantics:
+ * level draw, efc-wide beam per level, heuristic neighbour selection, reverse links with re-pruning). */
+LB200_EXPORT void lb200_build(lb200_index_t, lb200_error_t* error);
+
+/* ---- search path: usearch.h:277-296, lib.cpp:389-410 ------------------------------------------ */
+/* One query, host buffers.  Returns the number of matches written (ascending distance).
+ * continue_search (scan.c:273-281 streaming) is not implemented on the GPU: must be false. */
+LB200_EXPORT size_t lb200_search_ef(lb200_index_t, void const* query_vector, lb200_scalar_kind_t query_kind, size_t count,
+                                    size_t ef, bool continue_search, lb200_key_t* keys, lb200_distance_t* distances,
+                                    lb200_error_t* error);
+LB200_EXPORT size_t lb200_search(lb200_index_t, void const* query_vector, lb200_scalar_kind_t query_kind, size_t count,
+                                 lb200_key_t* keys, lb200_distance_t* distances, lb200_error_t* error);
+/* Batch of nq queries in HOST memory, `stride` bytes apart; outputs keys[nq][count], distances[nq][count]
+ * (unused tail: key UINT64_MAX, distance +inf), counts[nq] (may be NULL).  Host<->device copies included. */
+LB200_EXPORT void lb200_search_batch(lb200_index_t, void const* queries, size_t nq, size_t stride,
+                                     lb200_scalar_kind_t query_kind, size_t count, size_t ef, lb200_key_t* keys,
+                                     lb200_distance_t* distances, size_t* counts, lb200_error_t* error);
+/* Same with queries and outputs resident in DEVICE memory (counts: uint32_t[nq] or NULL); asynchronous on
+ * `cuda_stream` (a cudaStream_t passed as void*; NULL = default stream). */
+LB200_EXPORT void lb200_search_batch_device(lb200_index_t, void const* d_queries, size_t nq, size_t stride,
+                                            lb200_scalar_kind_t query_kind, size_t count, size_t ef,
+                                            lb200_key_t* d_keys, lb200_distance_t* d_distances, uint32_t* d_counts,
+                                            void* cuda_stream, lb200_error_t* error);
+LB200_EXPORT void lb200_last_search_stats(lb200_index_t, lb200_search_stats_t* stats, lb200_error_t* error);
+
+/* ---- (de)serialisation in the usearch/lantern file format: usearch.h:152-212, SURVEY App. B ----- */
+LB200_EXPORT size_t lb200_serialized_length(lb200_index_t, lb200_error_t* error); /* exact */
+LB200_EXPORT void lb200_save_buffer(lb200_index_t, void* buffer, size_t length, lb200_error_t* error);
+LB200_EXPORT void lb200_load_buffer(lb200_index_t, void const* buffer, size_t length, lb200_error_t* error);
+LB200_EXPORT void lb200_view_buffer(lb200_index_t, void const* buffer, size_t length, lb200_error_t* error);
+LB200_EXPORT void lb200_save(lb200_index_t, char const* path, lb200_error_t* error);
+LB200_EXPORT void lb200_load(lb200_index_t, char const* path, lb200_error_t* error);
+LB200_EXPORT void lb200_view(lb200_index_t, char const* path, lb200_error_t* error);
+LB200_EXPORT void lb200_metadata_buffer(void const* buffer, size_t length, lb200_init_options_t* options,
+                                        lb200_error_t* error);
+LB200_EXPORT uint64_t lb200_header_get_entry_slot(char* headerp);               /* lib.cpp:219-225 */
+LB200_EXPORT void lb200_header_set_entry_slot(char* headerp, uint64_t entry_slot); /* lib.cpp:227-231 */
+
+/* ---- stateless kernels: usearch.h:338-387 ------------------------------------------------------ */
+LB200_EXPORT lb200_distance_t lb200_distance(void const* vector_first, void const* vector_second,
+                                             lb200_scalar_kind_t scalar_kind, size_t dimensions,
+                                             lb200_metric_kind_t metric_kind, lb200_error_t* error);
+/* n pairs at once: a[i] vs b[i], host memory, strides in bytes. */
+LB200_EXPORT void lb200_distance_batch(void const* a, size_t a_stride, void const* b, size_t b_stride, size_t n,
+                                       lb200_scalar_kind_t scalar_kind, size_t dimensions,
+                                       lb200_metric_kind_t metric_kind, lb200_distance_t* out, lb200_error_t* error);
+/* Brute force (lib.cpp:450-481): keys receive DATASET OFFSETS, ascending distance; host memory. */
+LB200_EXPORT void lb200_exact_search(void const* dataset, size_t dataset_size, size_t dataset_stride,
+                                     void const* queries, size_t queries_size, size_t queries_stride,
+                                     lb200_scalar_kind_t scalar_kind, size_t dimensions, lb200_metric_kind_t metric_kind,
+                                     size_t count, size_t threads, lb200_key_t* keys, size_t keys_stride,
+                                     lb200_distance_t* distances, size_t distances_stride, lb200_error_t* error);
+/* Same, inputs/outputs in device memory (rows densely packed in `scalar_kind`). */
+LB200_EXPORT void lb200_exact_search_device(void const* d_dataset, size_t dataset_size, size_t dataset_stride,
+                                            void const* d_queries, size_t queries_size, size_t queries_stride,
+                                            lb200_scalar_kind_t scalar_kind, size_t dimensions,
+                                            lb200_metric_kind_t metric_kind, size_t count, lb200_key_t* d_keys,
+                                            lb200_distance_t* d_distances, void* cuda_stream, lb200_error_t* error);
+/* f32 -> f16 / i8 / b1 (index_plugins.hpp:879-974); host memory; `count` vectors. */
+LB200_EXPORT void lb200_cast(lb200_scalar_kind_t from, void const* vectors, lb200_scalar_kind_t to, void* result,
+                             size_t result_size, int dims, lb200_error_t* error);
+LB200_EXPORT void lb200_cast_batch(void const* vectors_f32, size_t count, size_t dims, lb200_scalar_kind_t to,
+                                   void* result, lb200_error_t* error);
+
+/* ---- PQ codec (lantern_storage.hpp:100-149; quantize_vector / dequantize_vector in lantern.sql) -- */
+/* codebook float[num_centroids][dims]; codes uint8[count][num_subvectors].
+ * compat128 != 0 reproduces the reference index's signed-char loop (only centroids 0..127). */
+LB200_EXPORT void lb200_quantize_pq(float const* codebook, size_t dims, size_t num_centroids, size_t num_subvectors,
+                                    float const* vectors, size_t count, uint8_t* codes, int compat128,
+                                    lb200_error_t* error);
+LB200_EXPORT void lb200_dequantize_pq(float const* codebook, size_t dims, size_t num_centroids, size_t num_subvectors,
+                                      uint8_t const* codes, size_t count, float* vectors, lb200_error_t* error);
+
+/* ---- multi-GPU epilogue: merge G per-shard top-k lists (already all-gathered) per query ---------- */
+/* d_keys/d_dists: [G][nq][count] on this device; outputs [nq][count]. */
+LB200_EXPORT void lb200_merge_shards_device(lb200_key_t const* d_keys, lb200_distance_t const* d_dists, size_t shards,
+                                            size_t nq, size_t count, lb200_key_t* d_out_keys,
+                                            lb200_distance_t* d_out_dists, void* cuda_stream, lb200_error_t* error);
+
+/* ---- engine info ------------------------------------------------------------------------------- */
+LB200_EXPORT int lb200_device_count(void);
+LB200_EXPORT char const* lb200_version(void);
+/* number of engine kernels launched by this process so far (bench.py's gpu_launches) */
+LB200_EXPORT uint64_t lb200_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LANTERN_B200_H */

@@ -1,0 +1,327 @@
+// lantern_b200 -- Index: device memory management and the host side of search.
+//
+// Host-side mirror of what index_dense_gt does around the hot path
+// (U/include/usearch/index_dense.hpp:1395-1451: cast the incoming vector to the storage scalar kind,
+// pick expansion = max(ef, k), run the search, dump keys+distances), for whole batches.
+#include "engine.h"
+
+#include <string.h>
+
+#include <algorithm>
+
+#include "distance.cuh"
+
+namespace lb200 {
+
+std::atomic<uint64_t> g_kernel_launches{0};
+
+int device_sm_count() {
+    static int sms = -1;
+    if (sms < 0) {
+        int dev = 0;
+        LB_CUDA(cudaGetDevice(&dev));
+        LB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    return sms;
+}
+
+void require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        throw CudaError("CUDA device unavailable: lantern_b200 has no CPU fallback");
+    }
+}
+
+namespace {
+
+__global__ void fill_results_kernel(uint64_t* keys, float* dists, uint32_t* counts, size_t nq, size_t k) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq * k)
+        keys[i] = ~0ull, dists[i] = INFINITY;
+    if (counts && i < nq)
+        counts[i] = 0;
+}
+
+template <typename T> void grow_device(T*& ptr, size_t old_count, size_t new_count, int fill_byte) {
+    T* np = nullptr;
+    LB_CUDA(cudaMalloc(&np, std::max<size_t>(new_count, 1) * sizeof(T)));
+    if (fill_byte >= 0)
+        LB_CUDA(cudaMemset(np, fill_byte, std::max<size_t>(new_count, 1) * sizeof(T)));
+    if (ptr && old_count)
+        LB_CUDA(cudaMemcpy(np, ptr, old_count * sizeof(T), cudaMemcpyDeviceToDevice));
+    if (ptr)
+        LB_CUDA(cudaFree(ptr));
+    ptr = np;
+}
+
+} // namespace
+
+Index::Index(const IndexConfig& cfg, const float* codebook) : cfg_(cfg) {
+    dist_mode_ = distance_mode(cfg.metric_kind, cfg.scalar_kind);
+    vec_bytes_ = scalar_row_bytes(cfg.scalar_kind, cfg.dims);
+    if (cfg.pq) {
+        stored_bytes_ = cfg.num_subvectors;
+        row_bytes_ = round_up(cfg.num_subvectors, 16);
+        LB_CUDA(cudaMalloc(&d_codebook_, cfg.num_centroids * cfg.dims * sizeof(float)));
+        LB_CUDA(cudaMemcpy(d_codebook_, codebook, cfg.num_centroids * cfg.dims * sizeof(float), cudaMemcpyHostToDevice));
+    } else {
+        stored_bytes_ = vec_bytes_;
+        row_bytes_ = round_up(vec_bytes_, 16);
+    }
+    LB_CUDA(cudaMalloc(&scratch_.counters, 4 * sizeof(unsigned long long)));
+    LB_CUDA(cudaMemset(scratch_.counters, 0, 4 * sizeof(unsigned long long)));
+}
+
+Index::~Index() {
+    cudaFree(d_vectors_), cudaFree(d_adj0_), cudaFree(d_upper_ref_), cudaFree(d_upper_adj_), cudaFree(d_keys_);
+    cudaFree(d_codebook_), cudaFree(scratch_.visited), cudaFree(scratch_.touched), cudaFree(scratch_.counters);
+    cudaFree(d_query_buf_), cudaFree(d_io_buf_);
+    if (h_pinned_)
+        cudaFreeHost(h_pinned_);
+}
+
+void Index::ensure_capacity(size_t cap) {
+    if (cap <= capacity_)
+        return;
+    size_t nc = std::max(cap, capacity_ + capacity_ / 2);
+    nc = round_up(nc, 32);
+    const size_t used = n_ + pending_n_;
+    grow_device(d_vectors_, used * row_bytes_, nc * row_bytes_, 0);
+    grow_device(d_adj0_, n_ * cfg_.M0, nc * cfg_.M0, 0xFF);
+    grow_device(d_upper_ref_, n_, nc, 0xFF);
+    grow_device(d_keys_, n_, nc, 0xFF);
+    capacity_ = nc;
+}
+
+void Index::reserve(size_t capacity) {
+    std::lock_guard<std::mutex> g(mu_);
+    ensure_capacity(capacity);
+}
+
+void Index::alloc_upper(size_t total_lists) {
+    if (total_lists <= upper_lists_cap_)
+        return;
+    size_t nc = std::max(total_lists, upper_lists_cap_ + upper_lists_cap_ / 2);
+    grow_device(d_upper_adj_, upper_lists_ * cfg_.M, nc * cfg_.M, 0xFF);
+    upper_lists_cap_ = nc;
+}
+
+void* Index::io_buffer(size_t bytes) {
+    if (bytes > io_buf_bytes_) {
+        if (d_io_buf_)
+            LB_CUDA(cudaFree(d_io_buf_));
+        d_io_buf_ = nullptr;
+        io_buf_bytes_ = round_up(bytes + bytes / 4, 256);
+        LB_CUDA(cudaMalloc(&d_io_buf_, io_buf_bytes_));
+    }
+    return d_io_buf_;
+}
+
+uint8_t* Index::query_buffer(size_t bytes) {
+    if (bytes > query_buf_bytes_) {
+        if (d_query_buf_)
+            LB_CUDA(cudaFree(d_query_buf_));
+        d_query_buf_ = nullptr;
+        query_buf_bytes_ = round_up(bytes + bytes / 4, 256);
+        LB_CUDA(cudaMalloc(&d_query_buf_, query_buf_bytes_));
+    }
+    return d_query_buf_;
+}
+
+void* Index::pinned(size_t bytes) {
+    if (bytes > pinned_bytes_) {
+        if (h_pinned_)
+            LB_CUDA(cudaFreeHost(h_pinned_));
+        h_pinned_ = nullptr;
+        pinned_bytes_ = round_up(bytes + bytes / 4, 4096);
+        LB_CUDA(cudaMallocHost(&h_pinned_, pinned_bytes_));
+    }
+    return h_pinned_;
+}
+
+// ---- staging of new vectors (usearch_add: U/c/lib.cpp:357-365 -> index_dense.hpp:1395-1426) ---------
+static void check_input_kind(const IndexConfig& cfg, int kind) {
+    if (kind == SK_F32) {
+        if (cfg.metric_kind == MK_HAMMING && cfg.scalar_kind == SK_B1)
+            return; // f32 -> sign bits is what cast_gt does; allowed
+        return;
+    }
+    if (kind == SK_B1 && cfg.scalar_kind == SK_B1)
+        return;
+    throw CudaError("vectors must be passed as f32, or as packed bits (b1) for a b1 index");
+}
+
+void Index::add_device(const uint64_t* host_keys, const void* d_vectors, size_t n, size_t stride, int kind) {
+    std::lock_guard<std::mutex> g(mu_);
+    check_input_kind(cfg_, kind);
+    if (!n)
+        return;
+    for (size_t i = 0; i < n; ++i)
+        if (host_keys[i] == ~0ull)
+            throw CudaError("key UINT64_MAX is reserved (free key)");
+    const size_t used = n_ + pending_n_;
+    ensure_capacity(used + n);
+    if (cfg_.pq) {
+        if (kind != SK_F32)
+            throw CudaError("pq index takes f32 vectors");
+        launch_pq_encode(d_codebook_, cfg_.dims, cfg_.num_centroids, cfg_.num_subvectors, (const float*)d_vectors,
+                         stride / sizeof(float), n, d_vectors_ + used * row_bytes_, row_bytes_, /*compat128=*/true, 0);
+        // zero padding of the code rows was done by ensure_capacity's memset
+    } else {
+        launch_cast_rows(d_vectors, stride, kind, d_vectors_ + used * row_bytes_, row_bytes_, cfg_.scalar_kind, cfg_.dims, n, 0);
+    }
+    h_keys_.insert(h_keys_.end(), host_keys, host_keys + n);
+    pending_n_ += n;
+}
+
+void Index::add_host(const uint64_t* keys, const void* vectors, size_t n, size_t stride, int kind) {
+    if (!n)
+        return;
+    check_input_kind(cfg_, kind);
+    const size_t in_bytes = scalar_row_bytes(kind, cfg_.dims);
+    void* d_tmp = nullptr;
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        d_tmp = io_buffer(n * in_bytes);
+        LB_CUDA(cudaMemcpy2D(d_tmp, in_bytes, vectors, stride, in_bytes, n, cudaMemcpyHostToDevice));
+    }
+    add_device(keys, d_tmp, n, in_bytes, kind);
+    LB_CUDA(cudaDeviceSynchronize());
+}
+
+void Index::build() {
+    std::lock_guard<std::mutex> g(mu_);
+    if (pending_n_)
+        build_pending(*this);
+}
+
+GraphView Index::view() const {
+    GraphView g{};
+    g.vectors = d_vectors_;
+    g.adj0 = d_adj0_;
+    g.upper_ref = d_upper_ref_;
+    g.upper_adj = d_upper_adj_;
+    g.keys = d_keys_;
+    g.n = (uint32_t)n_;
+    g.row_bytes = (uint32_t)row_bytes_;
+    g.M = (uint32_t)cfg_.M, g.M0 = (uint32_t)cfg_.M0;
+    g.entry = entry_;
+    g.max_level = max_level_;
+    g.codebook = d_codebook_;
+    g.dims = (uint32_t)cfg_.dims;
+    g.num_centroids = (uint32_t)cfg_.num_centroids;
+    g.num_subvectors = (uint32_t)cfg_.num_subvectors;
+    return g;
+}
+
+void Index::ensure_scratch(uint32_t ctas) {
+    const size_t words = round_up((capacity_ + 31) / 32, 32);
+    if (ctas <= scratch_.ctas && words <= scratch_.words_per_cta)
+        return;
+    if (scratch_.visited)
+        LB_CUDA(cudaFree(scratch_.visited));
+    if (scratch_.touched)
+        LB_CUDA(cudaFree(scratch_.touched));
+    scratch_.visited = nullptr, scratch_.touched = nullptr;
+    scratch_.ctas = std::max(ctas, scratch_.ctas);
+    scratch_.words_per_cta = words;
+    scratch_.touched_cap = 16384;
+    LB_CUDA(cudaMalloc(&scratch_.visited, (size_t)scratch_.ctas * words * sizeof(uint32_t)));
+    LB_CUDA(cudaMemset(scratch_.visited, 0, (size_t)scratch_.ctas * words * sizeof(uint32_t)));
+    LB_CUDA(cudaMalloc(&scratch_.touched, (size_t)scratch_.ctas * scratch_.touched_cap * sizeof(uint32_t)));
+}
+
+void Index::search_device(const void* d_queries, size_t nq, size_t stride, int kind, size_t k, size_t ef, uint64_t* d_keys,
+                          float* d_dists, uint32_t* d_counts, cudaStream_t stream) {
+    std::lock_guard<std::mutex> g(mu_);
+    check_input_kind(cfg_, kind);
+    if (!nq || !k)
+        return;
+    if (pending_n_)
+        build_pending(*this);
+    if (n_ == 0) { // index.hpp:2693: empty index -> no results
+        size_t total = std::max(nq * k, nq);
+        fill_results_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_keys, d_dists, d_counts, nq, k);
+        LB_CUDA(cudaGetLastError());
+        count_launch();
+        last_nq_ = 0;
+        return;
+    }
+    size_t L = ef ? ef : cfg_.ef; // usearch.h:265-271: 0 = index default
+    if (L < k)
+        L = k; // index.hpp:2706
+    if (L > 4096)
+        throw CudaError("search: max(ef, count) > 4096 is not supported");
+    if (cfg_.pq)
+        throw CudaError("search over a pq index: not implemented yet");
+
+    // queries -> storage scalar kind, 16-byte padded rows (index_dense.hpp:1435-1441)
+    uint8_t* qbuf = query_buffer(nq * row_bytes_);
+    launch_cast_rows(d_queries, stride, kind, qbuf, row_bytes_, cfg_.scalar_kind, cfg_.dims, nq, stream);
+
+    const uint32_t max_ctas = search_max_ctas(dist_mode_, cfg_.scalar_kind, (uint32_t)row_bytes_, (uint32_t)L, (uint32_t)cfg_.M0, false);
+    ensure_scratch(max_ctas);
+    LB_CUDA(cudaMemsetAsync(scratch_.counters, 0, 4 * sizeof(unsigned long long), stream));
+
+    SearchLaunch p{};
+    p.g = view();
+    p.s = scratch_;
+    p.s.ctas = max_ctas;
+    p.queries = qbuf;
+    p.query_stride = (uint32_t)row_bytes_;
+    p.nq = (uint32_t)nq, p.k = (uint32_t)k, p.L = (uint32_t)L;
+    p.out_keys = d_keys, p.out_dists = d_dists, p.out_counts = d_counts;
+    launch_search(dist_mode_, cfg_.scalar_kind, p, stream);
+    last_nq_ = (uint32_t)nq;
+}
+
+void Index::search_host(const void* queries, size_t nq, size_t stride, int kind, size_t k, size_t ef, uint64_t* keys,
+                        float* dists, size_t* counts) {
+    if (!nq || !k)
+        return;
+    check_input_kind(cfg_, kind);
+    const size_t in_bytes = scalar_row_bytes(kind, cfg_.dims);
+    uint8_t* base = nullptr;
+    size_t o_keys, o_dists, o_counts;
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        size_t o = round_up(nq * in_bytes, 256);
+        o_keys = o, o += round_up(nq * k * sizeof(uint64_t), 256);
+        o_dists = o, o += round_up(nq * k * sizeof(float), 256);
+        o_counts = o, o += round_up(nq * sizeof(uint32_t), 256);
+        base = (uint8_t*)io_buffer(o);
+    }
+    cudaStream_t stream = 0;
+    LB_CUDA(cudaMemcpy2DAsync(base, in_bytes, queries, stride, in_bytes, nq, cudaMemcpyHostToDevice, stream));
+    search_device(base, nq, in_bytes, kind, k, ef, (uint64_t*)(base + o_keys), (float*)(base + o_dists),
+                  (uint32_t*)(base + o_counts), stream);
+    LB_CUDA(cudaMemcpyAsync(keys, base + o_keys, nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    LB_CUDA(cudaMemcpyAsync(dists, base + o_dists, nq * k * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    std::vector<uint32_t> c32;
+    if (counts) {
+        c32.resize(nq);
+        LB_CUDA(cudaMemcpyAsync(c32.data(), base + o_counts, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    }
+    LB_CUDA(cudaStreamSynchronize(stream));
+    if (counts)
+        for (size_t i = 0; i < nq; ++i)
+            counts[i] = c32[i];
+}
+
+SearchStats Index::last_stats() {
+    std::lock_guard<std::mutex> g(mu_);
+    unsigned long long c[4] = {0, 0, 0, 0};
+    LB_CUDA(cudaDeviceSynchronize());
+    LB_CUDA(cudaMemcpy(c, scratch_.counters, sizeof(c), cudaMemcpyDeviceToHost));
+    SearchStats s;
+    s.queries = last_nq_;
+    s.computed_distances = c[1], s.base_pops = c[2], s.upper_hops = c[3];
+    // B_alg = n_dist*bytes_per_stored_vector + n_pop*(4 + M_level*4) + query bytes
+    s.algorithmic_bytes = s.computed_distances * (cfg_.pq ? stored_bytes_ : vec_bytes_) + s.base_pops * (4 + 4 * cfg_.M0) +
+                          s.upper_hops * (4 + 4 * cfg_.M) + s.queries * vec_bytes_;
+    return s;
+}
+
+} // namespace lb200

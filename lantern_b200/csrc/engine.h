@@ -1,0 +1,180 @@
+// lantern_b200 -- host-side index object behind the C ABI (include/lantern_b200.h).
+//
+// HBM layout of one index (one shard = one GPU):
+//   vectors   [capacity][row_bytes]   stored scalar kind (f32/f16/i8/b1), row_bytes = round_up(bytes,16),
+//                                     zero padded; base 256-B aligned -> every row is a whole number of
+//                                     16-B chunks and (for d=768 f32) of 128-B lines.   PQ: codes[capacity][nsub_pad]
+//   adj0      [capacity][M0] u32      level-0 adjacency, stored order, padded with 0xFFFFFFFF
+//   upper_ref [capacity] u32          0xFFFFFFFF for level-0-only nodes, else offset/M into upper_adj of the node's
+//                                     level-1 list; level l list at (ref + l-1)*M
+//   upper_adj [sum(levels)*M] u32     padded with 0xFFFFFFFF
+//   keys      [capacity] u64, levels [capacity] i16
+//   scratch   per resident CTA: visited bitmap (capacity bits) + touched-word list
+// The reference keeps the same information in per-node byte tapes with 6-byte slots
+// (U/include/usearch/index.hpp:1799-1863); only the (de)serialiser here speaks that format.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace lb200 {
+
+struct IndexConfig {
+    int metric_kind = MK_L2SQ;
+    int scalar_kind = SK_F32;
+    size_t dims = 0;
+    size_t M = 16, M0 = 32, efc = 128, ef = 64;
+    bool pq = false;
+    size_t num_centroids = 0, num_subvectors = 0;
+};
+
+struct SearchStats {
+    uint64_t queries = 0, computed_distances = 0, base_pops = 0, upper_hops = 0, algorithmic_bytes = 0;
+};
+
+// Device-side view handed to kernels (plain pointers, trivially copyable).
+struct GraphView {
+    const uint8_t* vectors;
+    const uint32_t* adj0;
+    const uint32_t* upper_ref;
+    const uint32_t* upper_adj;
+    const uint64_t* keys;
+    uint32_t n;
+    uint32_t row_bytes; // bytes per stored row (multiple of 16)
+    uint32_t M, M0;
+    uint32_t entry;
+    int32_t max_level;
+    // PQ (row_bytes then is the padded code width)
+    const float* codebook; // [num_centroids][dims]
+    uint32_t dims, num_centroids, num_subvectors;
+};
+
+struct SearchScratch {
+    uint32_t* visited;     // [ctas][words_per_cta]
+    uint32_t* touched;     // [ctas][touched_cap]
+    unsigned long long* counters; // [0]=next query, [1]=dist evals, [2]=base pops, [3]=upper hops
+    size_t words_per_cta;
+    uint32_t touched_cap;
+    uint32_t ctas;
+};
+
+class Index {
+  public:
+    explicit Index(const IndexConfig& cfg, const float* codebook);
+    ~Index();
+
+    const IndexConfig& config() const { return cfg_; }
+    size_t size() const { return n_ + pending_n_; }
+    size_t capacity() const { return capacity_; }
+    size_t row_bytes() const { return row_bytes_; }
+
+    void reserve(size_t capacity);
+    // staging (host or device source) of vectors in the *input* kind (f32 or b1)
+    void add_host(const uint64_t* keys, const void* vectors, size_t n, size_t stride, int kind);
+    void add_device(const uint64_t* host_keys, const void* d_vectors, size_t n, size_t stride, int kind);
+    void build(); // insert all pending vectors (build.cu)
+
+    // search: queries in device memory, input kind f32 or b1
+    void search_device(const void* d_queries, size_t nq, size_t stride, int kind, size_t k, size_t ef, uint64_t* d_keys,
+                       float* d_dists, uint32_t* d_counts, cudaStream_t stream);
+    void search_host(const void* queries, size_t nq, size_t stride, int kind, size_t k, size_t ef, uint64_t* keys,
+                     float* dists, size_t* counts);
+    SearchStats last_stats();
+
+    // usearch/lantern file format (format.cc)
+    size_t serialized_length();
+    size_t save_buffer(void* buffer, size_t length);
+    void load_buffer(const void* buffer, size_t length);
+
+    GraphView view() const;
+
+    // --- used by build.cu / format.cc ---
+    void ensure_capacity(size_t cap);
+    void alloc_upper(size_t total_lists);
+
+    IndexConfig cfg_;
+    int dist_mode_ = 0;
+    size_t row_bytes_ = 0;    // stored row (or padded PQ code) bytes
+    size_t vec_bytes_ = 0;    // unpadded bytes of a vector in the metric scalar kind (file format)
+    size_t stored_bytes_ = 0; // unpadded bytes kept per node in the file (vec_bytes_ or num_subvectors)
+    size_t n_ = 0, capacity_ = 0;
+    int32_t max_level_ = -1;
+    uint32_t entry_ = 0;
+    uint64_t level_rng_ = 0x9E3779B97F4A7C15ull;
+
+    // device arrays
+    uint8_t* d_vectors_ = nullptr;
+    uint32_t* d_adj0_ = nullptr;
+    uint32_t* d_upper_ref_ = nullptr;
+    uint32_t* d_upper_adj_ = nullptr;
+    size_t upper_lists_ = 0, upper_lists_cap_ = 0; // number of M-wide lists in d_upper_adj_
+    uint64_t* d_keys_ = nullptr;
+    float* d_codebook_ = nullptr;
+    // host mirrors of the small per-node metadata
+    std::vector<int16_t> h_levels_;
+    std::vector<uint64_t> h_keys_;
+
+    // pending (not yet inserted) vectors live directly in d_vectors_[n_ ...); only bookkeeping here
+    size_t pending_n_ = 0;
+
+    // search scratch
+    SearchScratch scratch_{};
+    size_t scratch_capacity_ = 0;
+    uint8_t* d_query_buf_ = nullptr;
+    size_t query_buf_bytes_ = 0;
+    void* d_io_buf_ = nullptr;
+    size_t io_buf_bytes_ = 0;
+    void* h_pinned_ = nullptr;
+    size_t pinned_bytes_ = 0;
+    SearchStats last_stats_{};
+    uint32_t last_nq_ = 0;
+    std::mutex mu_;
+
+    void ensure_scratch(uint32_t ctas);
+    void* io_buffer(size_t bytes);
+    void* pinned(size_t bytes);
+    uint8_t* query_buffer(size_t bytes);
+};
+
+// ---- kernels' host launchers -----------------------------------------------------------------------
+// codec.cu
+void launch_cast_rows(const void* d_in, size_t in_stride, int in_kind, void* d_out, size_t out_stride, int out_kind,
+                      size_t dims, size_t n, cudaStream_t stream);
+void launch_pq_encode(const float* d_codebook, size_t dims, size_t ncent, size_t nsub, const float* d_vecs,
+                      size_t vec_stride_floats, size_t n, uint8_t* d_codes, size_t code_stride, bool compat128,
+                      cudaStream_t stream);
+void launch_pq_decode(const float* d_codebook, size_t dims, size_t ncent, size_t nsub, const uint8_t* d_codes,
+                      size_t code_stride, size_t n, float* d_vecs, cudaStream_t stream);
+// search.cu
+struct SearchLaunch {
+    GraphView g;
+    SearchScratch s;
+    const uint8_t* queries; // storage kind, stride = query_stride
+    uint32_t query_stride;
+    uint32_t nq, k, L;
+    uint64_t* out_keys;
+    float* out_dists;
+    uint32_t* out_counts;
+};
+uint32_t search_max_ctas(int dist_mode, int scalar_kind, uint32_t row_bytes, uint32_t L, uint32_t M0, bool pq);
+void launch_search(int dist_mode, int scalar_kind, const SearchLaunch& p, cudaStream_t stream);
+// exact.cu
+void launch_exact(int dist_mode, int scalar_kind, const uint8_t* d_data, size_t n, size_t data_stride,
+                  const uint8_t* d_queries, size_t nq, size_t q_stride, uint32_t row_bytes, size_t k, uint64_t* d_keys,
+                  float* d_dists, cudaStream_t stream);
+void launch_pair_distance(int dist_mode, int scalar_kind, const uint8_t* d_a, size_t a_stride, const uint8_t* d_b,
+                          size_t b_stride, size_t n, uint32_t row_bytes, float* d_out, cudaStream_t stream);
+void launch_merge_shards(const uint64_t* d_keys, const float* d_dists, size_t shards, size_t nq, size_t k,
+                         uint64_t* d_out_keys, float* d_out_dists, cudaStream_t stream);
+// build.cu
+void build_pending(Index& idx);
+
+int device_sm_count();
+void require_device();
+
+} // namespace lb200

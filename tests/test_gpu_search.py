@@ -1,0 +1,117 @@
+"""GPU parity: the CUDA search path (through the C ABI) against the oracle ON THE SAME GRAPH.
+
+The graph is built by the CPU oracle (hnsw_oracle.c, itself pinned byte-for-byte against the
+reference), serialised in the usearch/lantern file format and loaded with lb200_load_buffer --
+exactly how Lantern's scan path hands an index to usearch (scan.c:99-110)."""
+import numpy as np
+import pytest
+
+from util import build_port_index, compare_results, structured
+
+pytestmark = pytest.mark.gpu
+
+
+def _roundtrip(eng, port, X, Q, metric, quant, M, efc, ef, k, exact_ids=True):
+    pidx = build_port_index(port, X, metric, quant, M=M, efc=efc, ef=ef)
+    buf = pidx.save_buffer()
+    dim = X.shape[1] * 8 if X.dtype == np.uint8 else X.shape[1]
+    g = eng.Index(dim, metric, quant, M=M, efc=efc, ef=ef)
+    g.load_buffer(buf)
+    assert g.size() == len(X)
+    gk, gd, gc = g.search_batch(Q, k)
+    pk, pd, pc, tot = pidx.search_batch(Q, k)
+    assert np.array_equal(gc.astype(np.int64), pc)
+    st = g.last_stats()
+    return gk, gd, pk, pd, st, tot, g, pidx
+
+
+def test_small_world_cube(eng, port):
+    cube = np.array([[0, 0, 0], [0, 0, 1], [0, 1, 0], [0, 1, 1], [1, 0, 0], [1, 0, 1], [1, 1, 0], [1, 1, 1]], np.float32)
+    Q = np.array([[0, 1, 0]], np.float32)
+    gk, gd, pk, pd, st, tot, g, p = _roundtrip(eng, port, cube, Q, "l2sq", "f32", 2, 128, 4, 8)
+    assert np.array_equal(gd[0], np.array([0, 1, 1, 1, 2, 2, 2, 3], np.float32))
+    assert np.array_equal(np.sort(gk[0]), np.arange(1, 9))
+    assert gk[0][0] == 3  # vertex 010
+
+
+@pytest.mark.parametrize("metric,quant,d", [("l2sq", "f32", 64), ("cos", "f32", 96), ("l2sq", "f32", 768), ("cos", "f32", 100),
+                                            ("l2sq", "f16", 128), ("cos", "f16", 72), ("l2sq", "i8", 128), ("cos", "i8", 80),
+                                            ("l2sq", "f32", 3), ("l2sq", "f32", 1536)])
+def test_same_graph_same_ids(eng, port, metric, quant, d):
+    n = 3000 if d <= 768 else 1500
+    X = structured(n, d, seed=7)
+    Q = structured(200, d, seed=8)
+    if quant == "i8":
+        X, Q = X * 0.3, Q * 0.3
+    gk, gd, pk, pd, st, tot, g, p = _roundtrip(eng, port, X, Q, metric, quant, 16, 128, 64, 10)
+    assert np.allclose(gd, pd, rtol=1e-5, atol=1e-6), np.abs(gd - pd).max()
+    exact, ok = compare_results(gk, gd, pk, pd)
+    assert ok == len(Q), (exact, ok)
+    assert exact >= 0.97 * len(Q), exact
+    # work counters are the reference's own (index.hpp:2726): identical decisions -> identical counts
+    if exact == len(Q):
+        assert st["computed_distances"] == tot["computed_distances"]
+        assert st["base_pops"] == tot["base_pops"]
+        assert st["upper_hops"] == tot["upper_hops"]
+
+
+def test_integer_data_ties(eng, port):
+    """Integer-valued vectors: every fp32 sum is exact whatever the order, but exact distance TIES are frequent;
+    only the order in which equal-distance candidates leave the queue may differ."""
+    rng = np.random.default_rng(3)
+    X = rng.integers(-8, 9, (4000, 48)).astype(np.float32)
+    Q = rng.integers(-8, 9, (300, 48)).astype(np.float32)
+    gk, gd, pk, pd, st, tot, g, p = _roundtrip(eng, port, X, Q, "l2sq", "f32", 8, 64, 40, 10)
+    assert np.array_equal(gd[:, 0], pd[:, 0])
+    assert np.mean(gd == pd) > 0.98
+    exact, ok = compare_results(gk, gd, pk, pd)
+    assert exact >= 0.9 * len(Q)
+
+
+def test_hamming_bits(eng, port):
+    rng = np.random.default_rng(5)
+    protos = rng.integers(0, 256, (16, 96), dtype=np.uint8)
+    def gen(n, seed):
+        r = np.random.default_rng(seed)
+        base = protos[r.integers(0, 16, n)]
+        flips = (r.random((n, 96 * 8)) < 0.1)
+        return base ^ np.packbits(flips, axis=1)
+    X, Q = gen(3000, 1), gen(100, 2)
+    gk, gd, pk, pd, st, tot, g, p = _roundtrip(eng, port, X, Q, "hamming", "b1", 16, 128, 64, 10)
+    # heavy ties: compare the distance profile (tie order inside the candidate queue may differ)
+    assert np.array_equal(gd[:, 0], pd[:, 0])
+    assert np.mean(gd == pd) > 0.98
+
+
+def test_k_larger_than_ef_and_small_index(eng, port):
+    X = structured(50, 32, seed=1)
+    Q = structured(20, 32, seed=2)
+    gk, gd, pk, pd, st, tot, g, p = _roundtrip(eng, port, X, Q, "l2sq", "f32", 4, 16, 8, 40)  # expansion = max(ef,k)
+    exact, ok = compare_results(gk, gd, pk, pd)
+    assert ok == len(Q)
+    k1, d1 = g.search(Q[0], 5, ef=100)  # single-query entry point, ef honoured
+    k2, d2, _ = p.search(Q[0], 5, ef=100)
+    assert np.array_equal(k1, k2)
+
+
+def test_exhaustive_ef_matches_brute_force(eng, port):
+    """ef -> infinity: graph search with ef >= N equals brute force (bit-exact ids) on a connected graph."""
+    X = structured(1200, 40, seed=11)
+    Q = structured(50, 40, seed=12)
+    pidx = build_port_index(port, X, "l2sq", "f32", M=16, efc=128, ef=1200)
+    g = eng.Index(40, "l2sq", "f32", M=16, efc=128, ef=1200)
+    g.load_buffer(pidx.save_buffer())
+    gk, gd, _ = g.search_batch(Q, 10)
+    bk, bd = eng.exact_search(X, Q, 10, "l2sq")
+    assert np.array_equal(gk, bk + 1)  # keys are offset+1
+    assert np.allclose(gd, bd, rtol=1e-5)
+
+
+def test_save_load_roundtrip_bytes(eng, port):
+    X = structured(700, 24, seed=21)
+    pidx = build_port_index(port, X, "cos", "f32", M=6, efc=40, ef=20)
+    buf = pidx.save_buffer()
+    g = eng.Index(24, "cos", "f32", M=6, efc=40, ef=20)
+    g.load_buffer(buf)
+    out = g.save_buffer()
+    assert len(out) == len(buf) and np.array_equal(out, buf)
