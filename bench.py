@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py -- batched HNSW search throughput of the B200 engine (and of the reference on the host cores).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg2s]
+
+One "step" = one batch of queries through the hot path (greedy descent + ef-wide base-layer beam + top-k) over a
+synthetic corpus resident in HBM.  Workload (BASELINE.json configs[1], "cfg2"): 1 M x d768 fp32, structured synthetic
+(x = z P + 0.05 eps, 32-d latent), l2sq, M=16, ef_construction=128, ef=64, batch 1024, k=10, 1 x B200.
+The graph is built by the engine itself on the GPU (lb200_add_batch_device + lb200_build) before the timed region.
+
+`value`  : queries/s, queries already resident in HBM (lb200_search_batch_device), CUDA events on the launching stream.
+`e2e`    : the same through the reference-facing host call (lb200_search_batch: pinned host buffers in and out,
+           H2D/D2H inside the timed region).
+`roofline`: algorithmic bytes (n_dist*row_bytes + pops*(4+4*M0) + hops*(4+4*M) + query bytes, counters
+           returned by the kernel itself and equal to usearch's computed_distances) / search-kernel device time,
+           against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+`cpu_baseline`: the UNMODIFIED reference (oracle/_ref, usearch compiled from /root/reference) on all host cores,
+           loading the very index file the engine wrote (usearch file format) and searching the same queries --
+           which also yields the full-size same-graph id parity reported under `parity`.
+--impl reference: the reference alone on the host cores: builds its own graph over a bounded prefix of the corpus
+           (sized for ~1 minute of multi-threaded adds) and searches the same query batches.
+Every step uses a fresh batch of queries; the corpus (3 GB) is far larger than L2 (126 MB).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n, dim, metric, M, efc, ef, batch, k, description)
+    "cfg2": dict(n=1_000_000, dim=768, metric="l2sq", M=16, efc=128, ef=64, batch=1024, k=10,
+                 desc="cfg2: 1M x d768 f32 l2sq, M=16 efc=128 ef=64, batch-1024 k=10"),
+    "cfg2s": dict(n=100_000, dim=768, metric="l2sq", M=16, efc=128, ef=64, batch=1024, k=10,
+                  desc="cfg2s (smoke-size): 100k x d768 f32 l2sq, M=16 efc=128 ef=64, batch-1024 k=10"),
+    "cfg3": dict(n=10_000_000, dim=768, metric="cos", M=32, efc=128, ef=128, batch=4096, k=10,
+                 desc="cfg3: 10M x d768 f32 cosine, M=32 efc=128 ef=128, batch-4096 k=10"),
+}
+METRIC_NAME = "queries/sec @ recall@10, d=768 fp32, 10M vectors, batch 4096, 1/2/4/8 B200"
+LATENT, NOISE = 32, 0.05
+SEED_P, SEED_CORPUS, SEED_QUERY = 1234, 42, 43
+
+
+# --------------------------------------------------------------------------------------- synthetic data
+def projection_np(dim):
+    return (np.random.default_rng(SEED_P).standard_normal((LATENT, dim)) / np.sqrt(LATENT)).astype(np.float32)
+
+
+def structured_np(n, dim, seed, chunk=100_000):
+    """Host generator (reference arm): x = z P + NOISE * eps."""
+    P = projection_np(dim)
+    out = np.empty((n, dim), np.float32)
+    rng = np.random.default_rng(seed)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        z = rng.standard_normal((hi - lo, LATENT), dtype=np.float32)
+        out[lo:hi] = z @ P + NOISE * rng.standard_normal((hi - lo, dim), dtype=np.float32)
+    return out
+
+
+def structured_torch(n, dim, seed, device, chunk=200_000):
+    """Device generator (our arm).  Same distribution as structured_np (different random stream)."""
+    import torch
+    P = torch.from_numpy(projection_np(dim)).to(device)
+    out = torch.empty((n, dim), dtype=torch.float32, device=device)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        z = torch.randn((hi - lo, LATENT), generator=g, device=device)
+        out[lo:hi] = z @ P
+        out[lo:hi] += NOISE * torch.randn((hi - lo, dim), generator=g, device=device)
+    return out
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def recall_at_k(found, truth):
+    hits = 0
+    for f, t in zip(found, truth):
+        hits += len(set(f.tolist()) & set(t.tolist()))
+    return hits / float(truth.size)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------- reference arm
+def run_reference(args, wl):
+    """The reference's own CPU path (oracle/_ref = usearch compiled unmodified) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import reflib
+    if not reflib.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liboracle_usearch.so missing (run oracle/Makefile)"}))
+        return
+    cores = reflib.lib().refx_hardware_threads()
+    # bounded sample: a prefix of the corpus the reference can index in about a minute with all cores
+    n_ref = int(min(wl["n"], max(20_000, 350 * cores * 60)))
+    if args.ref_rows:
+        n_ref = min(wl["n"], args.ref_rows)
+    X = structured_np(n_ref, wl["dim"], SEED_CORPUS)
+    nsteps = args.steps + args.warmup
+    Q = structured_np(nsteps * wl["batch"], wl["dim"], SEED_QUERY)
+    idx = reflib.RefIndex(wl["dim"], wl["metric"], M=wl["M"], efc=wl["efc"], ef=wl["ef"], threads=cores)
+    idx.reserve(n_ref)
+    t0 = time.perf_counter()
+    idx.add_batch(np.arange(1, n_ref + 1, dtype=np.uint64), X, threads=cores)
+    t_build = time.perf_counter() - t0
+    times = []
+    for s in range(nsteps):
+        q = Q[s * wl["batch"]:(s + 1) * wl["batch"]]
+        t0 = time.perf_counter()
+        keys, dists, counts, comp, vis = idx.search_batch(q, wl["k"], threads=cores)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = args.steps * wl["batch"] / total
+    sample = "reference builds its own graph over the first %d of %d corpus rows (%.0f s, %d threads); %d batches of %d queries" % (
+        n_ref, wl["n"], t_build, cores, args.steps, wl["batch"])
+    line = {
+        "impl": "reference", "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "corpus_rows_indexed": n_ref, "ef": wl["ef"], "k": wl["k"], "batch": wl["batch"]},
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "build_vectors_per_s": n_ref / t_build,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------- our arm
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from lantern_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    api.lib()
+
+    n, dim, k, ef, B = wl["n"], wl["dim"], wl["k"], wl["ef"], wl["batch"]
+    nsteps = args.steps + args.warmup
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+
+    # ---- corpus shard of this rank: contiguous row range ----
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    t0 = time.perf_counter()
+    X = structured_torch(n, dim, SEED_CORPUS, dev)[lo:hi].contiguous() if world > 1 else structured_torch(n, dim, SEED_CORPUS, dev)
+    Q = structured_torch(nsteps * B, dim, SEED_QUERY, dev)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t0
+
+    ef_shard = args.shard_ef if (world > 1 and args.shard_ef) else ef
+    idx = api.Index(dim, wl["metric"], "f32", M=wl["M"], efc=wl["efc"], ef=ef_shard)
+    idx.reserve(hi - lo)
+    keys_host = np.arange(lo + 1, hi + 1, dtype=np.uint64)  # global keys = row + 1
+    t0 = time.perf_counter()
+    idx.add_batch_device(keys_host, X.data_ptr(), hi - lo, dim * 4, "f32")
+    idx.build()
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+
+    stream = torch.cuda.current_stream()
+    out_keys = torch.empty((B, k), dtype=torch.int64, device=dev)
+    out_dists = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    if world > 1:
+        g_keys = torch.empty((world, B, k), dtype=torch.int64, device=dev)
+        g_dists = torch.empty((world, B, k), dtype=torch.float32, device=dev)
+        m_keys = torch.empty((B, k), dtype=torch.int64, device=dev)
+        m_dists = torch.empty((B, k), dtype=torch.float32, device=dev)
+
+    def step_device(s):
+        q = Q[s * B:(s + 1) * B]
+        idx.search_batch_device(q.data_ptr(), B, dim * 4, "f32", k, ef_shard, out_keys.data_ptr(), out_dists.data_ptr(),
+                                out_counts.data_ptr(), stream.cuda_stream)
+        if world > 1:  # the one exchange step: all-gather of per-shard top-k over NVLink, then a G-way merge
+            dist.all_gather_into_tensor(g_keys, out_keys)
+            dist.all_gather_into_tensor(g_dists, out_dists)
+            api.merge_shards_device(g_keys.data_ptr(), g_dists.data_ptr(), world, B, k, m_keys.data_ptr(), m_dists.data_ptr(),
+                                    stream.cuda_stream)
+            return m_keys
+        return out_keys
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- ground truth for recall (untimed): brute force on this rank's shard, merged like the search results ----
+    nrec = min(B, 1024)
+    tk = torch.empty((nrec, k), dtype=torch.int64, device=dev)
+    td = torch.empty((nrec, k), dtype=torch.float32, device=dev)
+    api.exact_search_device(X.data_ptr(), hi - lo, dim * 4, Q.data_ptr(), nrec, dim * 4, k, tk.data_ptr(), td.data_ptr(),
+                            wl["metric"], "f32", dim, stream.cuda_stream)
+    tk += lo + 1  # offsets -> global keys
+    if world > 1:
+        gk = torch.empty((world, nrec, k), dtype=torch.int64, device=dev)
+        gd = torch.empty((world, nrec, k), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(gk, tk)
+        dist.all_gather_into_tensor(gd, td)
+        tk2 = torch.empty_like(tk)
+        td2 = torch.empty_like(td)
+        api.merge_shards_device(gk.data_ptr(), gd.data_ptr(), world, nrec, k, tk2.data_ptr(), td2.data_ptr(), stream.cuda_stream)
+        tk = tk2
+    torch.cuda.synchronize()
+    truth = tk.cpu().numpy()
+
+    # ---- warm-up, then K timed steps on the device ----
+    for s in range(args.warmup):
+        res = step_device(s)
+        if s == 0:
+            torch.cuda.synchronize()
+            rec = recall_at_k(res[:nrec].cpu().numpy(), truth)
+    barrier()
+    launches0 = api.kernel_launches()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    alg_bytes, kern_ms, n_dist = 0, 0.0, 0
+    barrier()
+    ev[0].record(stream)
+    for s in range(args.warmup, nsteps):
+        step_device(s)
+        if args.per_step_stats:
+            st = idx.last_stats()
+            alg_bytes += st["algorithmic_bytes"]; kern_ms += st["kernel_ms"]; n_dist += st["computed_distances"]
+    ev[1].record(stream)
+    barrier()
+    ms = ev[0].elapsed_time(ev[1])
+    clocks = sampler.stop() if sampler else None
+    launches = api.kernel_launches() - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = args.steps * B / (ms / 1e3)
+
+    # ---- roofline of the search kernel: separate pass with per-step counters (the stats call synchronises) ----
+    alg_bytes, kern_ms, n_dist, pops = 0, 0.0, 0, 0
+    for s in range(args.warmup, nsteps):
+        q = Q[s * B:(s + 1) * B]
+        idx.search_batch_device(q.data_ptr(), B, dim * 4, "f32", k, ef_shard, out_keys.data_ptr(), out_dists.data_ptr(),
+                                out_counts.data_ptr(), stream.cuda_stream)
+        st = idx.last_stats()
+        alg_bytes += st["algorithmic_bytes"]; kern_ms += st["kernel_ms"]; n_dist += st["computed_distances"]; pops += st["base_pops"]
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (kern_ms / 1e3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "search_kernel_traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                traffic = json.load(f).get(wl["desc"].split(":")[0])
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "kernel": "hnsw_search_kernel<l2sq|cos,f32,NQ=6>",
+                "kernel_ms_per_step": kern_ms / args.steps, "algorithmic_bytes_per_step": alg_bytes / args.steps,
+                "dist_evals_per_query": n_dist / (args.steps * B), "pops_per_query": pops / (args.steps * B)}
+
+    # ---- e2e through the reference-facing host call: pinned host buffers in/out, copies inside the timed region ----
+    e2e = None
+    if world == 1:
+        hq = torch.empty((nsteps * B, dim), dtype=torch.float32).pin_memory()
+        hq.copy_(Q)
+        hk = torch.empty((B, k), dtype=torch.int64).pin_memory()
+        hd = torch.empty((B, k), dtype=torch.float32).pin_memory()
+        hc = torch.empty((B,), dtype=torch.int64).pin_memory()
+        for s in range(args.warmup):
+            idx.search_batch_raw(hq[s * B].data_ptr(), B, dim * 4, "f32", k, ef, hk.data_ptr(), hd.data_ptr(), hc.data_ptr())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s in range(args.warmup, nsteps):
+            idx.search_batch_raw(hq[s * B].data_ptr(), B, dim * 4, "f32", k, ef, hk.data_ptr(), hd.data_ptr(), hc.data_ptr())
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": args.steps * B / dt, "unit": "queries/s", "h2d_bytes_per_step": B * dim * 4,
+               "d2h_bytes_per_step": B * k * 8 + B * k * 4 + B * 4, "ms_per_step": 1e3 * dt / args.steps}
+
+    # ---- CPU baseline (rank 0, N=1): the unmodified reference on the host cores over the SAME index file ----
+    cpu_baseline, parity = None, None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import reflib
+        if reflib.available():
+            cores = reflib.lib().refx_hardware_threads()
+            t0 = time.perf_counter()
+            buf = idx.save_buffer()
+            ridx = reflib.RefIndex(dim, wl["metric"], M=wl["M"], efc=wl["efc"], ef=ef, threads=cores)
+            ridx.load_buffer(buf)
+            t_load = time.perf_counter() - t0
+            del buf
+            ridx._loaded = None
+            qh = Q[:nsteps * B].cpu().numpy()
+            spent, done, first = 0.0, 0, None
+            s = 0
+            while spent < args.cpu_seconds and s < nsteps:
+                qb = qh[s * B:(s + 1) * B]
+                t0 = time.perf_counter()
+                rkeys, rd, rc, comp, vis = ridx.search_batch(qb, k, threads=cores)
+                spent += time.perf_counter() - t0
+                done += B
+                if first is None:
+                    first = (rkeys, rd, comp)
+                s += 1
+            cpu_qps = done / spent
+            cpu_baseline = {"value": cpu_qps, "unit": "queries/s", "cores": cores, "kind": "reference",
+                            "sample": "unmodified usearch (oracle/_ref) loads the engine's %d-node index file (%.0f s) and searches "
+                                      "%d of the bench's query batches (%d queries, %.1f s) on %d threads" % (
+                                          n, t_load, s, done, spent, cores)}
+            # same-graph parity at full size: step-0 queries, ids position-wise
+            idx.search_batch_device(Q.data_ptr(), B, dim * 4, "f32", k, ef, out_keys.data_ptr(), out_dists.data_ptr(),
+                                    out_counts.data_ptr(), stream.cuda_stream)
+            torch.cuda.synchronize()
+            st0 = idx.last_stats()
+            gk = out_keys.cpu().numpy().astype(np.uint64)
+            gd = out_dists.cpu().numpy()
+            rk0, rd0, comp0 = first
+            parity = {"queries": B, "identical_id_rows": float(np.mean(np.all(gk == rk0, axis=1))),
+                      "identical_ids": float(np.mean(gk == rk0)),
+                      "max_rel_dist_err": float(np.max(np.abs(gd - rd0) / np.maximum(np.abs(rd0), 1e-12))),
+                      "reference_computed_distances": int(comp0), "engine_computed_distances": int(st0["computed_distances"]),
+                      "reference_recall_at_10": recall_at_k(rk0[:nrec], truth)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "corpus_rows": n, "rows_per_gpu": hi - lo, "ef": ef, "ef_per_shard": ef_shard, "k": k,
+                       "batch": B, "parallelism": "row-range shards x%d + NCCL all-gather of top-k + merge" % world if world > 1 else "1 GPU",
+                       "l2_policy": "inputs larger than L2: fresh query batch every step over a %.1f GB corpus" % ((hi - lo) * dim * 4 / 1e9),
+                       "generator": "x = z P + %.2f eps, z~N(0,I_%d), seeds %d/%d/%d" % (NOISE, LATENT, SEED_P, SEED_CORPUS, SEED_QUERY)},
+            "recall_at_10": rec, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "parity": parity,
+            "build": {"vectors_per_s": (hi - lo) / t_build, "seconds": t_build, "datagen_seconds": t_gen},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("LB200_WORKLOAD", "cfg2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--shard-ef", type=int, default=0, help="per-shard ef when --gpus > 1 (0 = the workload's ef)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="bound on the cpu_baseline search time")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-rows", type=int, default=0, help="--impl reference: corpus prefix to index (0 = auto by core count)")
+    ap.add_argument("--per-step-stats", action="store_true", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -109,6 +109,7 @@ typedef struct lb200_search_stats_t {
     uint64_t base_pops;          /* level-0 candidates expanded */
     uint64_t upper_hops;         /* level>=1 neighbour lists scanned */
     uint64_t algorithmic_bytes;  /* computed_distances*row_bytes + (base_pops*(4+4*M0) + upper_hops*(4+4*M)) + queries*row_bytes */
+    double kernel_ms;            /* device time of the search kernel alone (CUDA events on the launching stream) */
 } lb200_search_stats_t;
 
 /* ---- lifecycle: U/c/usearch.h:140-146, lib.cpp:130-176 ---------------------------------------- */
@@ -140,6 +141,12 @@ LB200_EXPORT void lb200_add_batch_device(lb200_index_t, lb200_key_t const* host_
 /* Inserts every staged vector into the HNSW graph on the GPU (index.hpp:2479-2564 semantics:
  * level draw, efc-wide beam per level, heuristic neighbour selection, reverse links with re-pruning). */
 LB200_EXPORT void lb200_build(lb200_index_t, lb200_error_t* error);
+
+/* Engine knobs that have no counterpart in usearch_init_options_t:
+ *   "build_batch"  max vectors inserted concurrently per batch (default 0 = one per resident CTA); 1 = strictly sequential insertion,
+ *                  i.e. the reference's order of operations (byte-identical graphs on order-independent data);
+ *   "build_ratio"  a batch never exceeds (nodes already in the graph) / build_ratio (default 64). */
+LB200_EXPORT void lb200_set_option(lb200_index_t, char const* name, size_t value, lb200_error_t* error);
 
 /* ---- search path: usearch.h:277-296, lib.cpp:389-410 ------------------------------------------ */
 /* One query, host buffers.  Returns the number of matches written (ascending distance).

@@ -54,7 +54,7 @@ class IndexMetadata(C.Structure):  # == usearch_index_metadata_t (usearch.h:119-
 
 class SearchStats(C.Structure):
     _fields_ = [("queries", C.c_uint64), ("computed_distances", C.c_uint64), ("base_pops", C.c_uint64),
-                ("upper_hops", C.c_uint64), ("algorithmic_bytes", C.c_uint64)]
+                ("upper_hops", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("kernel_ms", C.c_double)]
 
 
 ERRP = C.POINTER(C.c_char_p)
@@ -75,6 +75,7 @@ SIGNATURES = {
     "lb200_add_batch": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, ERRP]),
     "lb200_add_batch_device": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, ERRP]),
     "lb200_build": (None, [C.c_void_p, ERRP]),
+    "lb200_set_option": (None, [C.c_void_p, C.c_char_p, C.c_size_t, ERRP]),
     "lb200_search_ef": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_bool, C.c_void_p,
                                       C.c_void_p, ERRP]),
     "lb200_search": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, ERRP]),
@@ -214,6 +215,9 @@ class Index:
 
     def build(self):
         self._call("lb200_build")
+
+    def set_option(self, name, value):
+        self._call("lb200_set_option", name.encode(), int(value))
 
     def search(self, q, k, ef=0):
         q = np.ascontiguousarray(q)

@@ -212,6 +212,19 @@ LB200_EXPORT void lb200_build(lb200_index_t h, lb200_error_t* error) {
     guarded(error, [&] { as_index(h)->build(); });
 }
 
+LB200_EXPORT void lb200_set_option(lb200_index_t h, char const* name, size_t value, lb200_error_t* error) {
+    guarded(error, [&] {
+        Index* idx = as_index(h);
+        std::string n(name ? name : "");
+        if (n == "build_batch")
+            idx->build_batch_ = value;
+        else if (n == "build_ratio")
+            idx->build_ratio_ = value ? value : 1;
+        else
+            throw CudaError("unknown option");
+    });
+}
+
 LB200_EXPORT size_t lb200_search_ef(lb200_index_t h, void const* query, lb200_scalar_kind_t kind, size_t count, size_t ef,
                                     bool continue_search, lb200_key_t* keys, lb200_distance_t* distances, lb200_error_t* error) {
     size_t found = 0;
@@ -259,6 +272,7 @@ LB200_EXPORT void lb200_last_search_stats(lb200_index_t h, lb200_search_stats_t*
         stats->base_pops = s.base_pops;
         stats->upper_hops = s.upper_hops;
         stats->algorithmic_bytes = s.algorithmic_bytes;
+        stats->kernel_ms = s.kernel_ms;
     });
 }
 

@@ -72,6 +72,8 @@ Index::Index(const IndexConfig& cfg, const float* codebook) : cfg_(cfg) {
     }
     LB_CUDA(cudaMalloc(&scratch_.counters, 4 * sizeof(unsigned long long)));
     LB_CUDA(cudaMemset(scratch_.counters, 0, 4 * sizeof(unsigned long long)));
+    LB_CUDA(cudaEventCreate(&ev0_));
+    LB_CUDA(cudaEventCreate(&ev1_));
 }
 
 Index::~Index() {
@@ -80,6 +82,10 @@ Index::~Index() {
     cudaFree(d_query_buf_), cudaFree(d_io_buf_);
     if (h_pinned_)
         cudaFreeHost(h_pinned_);
+    if (ev0_)
+        cudaEventDestroy(ev0_);
+    if (ev1_)
+        cudaEventDestroy(ev1_);
 }
 
 void Index::ensure_capacity(size_t cap) {
@@ -273,7 +279,9 @@ void Index::search_device(const void* d_queries, size_t nq, size_t stride, int k
     p.query_stride = (uint32_t)row_bytes_;
     p.nq = (uint32_t)nq, p.k = (uint32_t)k, p.L = (uint32_t)L;
     p.out_keys = d_keys, p.out_dists = d_dists, p.out_counts = d_counts;
+    LB_CUDA(cudaEventRecord(ev0_, stream));
     launch_search(dist_mode_, cfg_.scalar_kind, p, stream);
+    LB_CUDA(cudaEventRecord(ev1_, stream));
     last_nq_ = (uint32_t)nq;
 }
 
@@ -317,6 +325,13 @@ SearchStats Index::last_stats() {
     LB_CUDA(cudaMemcpy(c, scratch_.counters, sizeof(c), cudaMemcpyDeviceToHost));
     SearchStats s;
     s.queries = last_nq_;
+    if (last_nq_) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess)
+            s.kernel_ms = ms;
+        else
+            (void)cudaGetLastError();
+    }
     s.computed_distances = c[1], s.base_pops = c[2], s.upper_hops = c[3];
     // B_alg = n_dist*bytes_per_stored_vector + n_pop*(4 + M_level*4) + query bytes
     s.algorithmic_bytes = s.computed_distances * (cfg_.pq ? stored_bytes_ : vec_bytes_) + s.base_pops * (4 + 4 * cfg_.M0) +

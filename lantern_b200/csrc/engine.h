@@ -35,6 +35,7 @@ struct IndexConfig {
 
 struct SearchStats {
     uint64_t queries = 0, computed_distances = 0, base_pops = 0, upper_hops = 0, algorithmic_bytes = 0;
+    double kernel_ms = 0; // device time of the search kernel alone (CUDA events on the launching stream)
 };
 
 // Device-side view handed to kernels (plain pointers, trivially copyable).
@@ -105,7 +106,11 @@ class Index {
     size_t n_ = 0, capacity_ = 0;
     int32_t max_level_ = -1;
     uint32_t entry_ = 0;
-    uint64_t level_rng_ = 0x9E3779B97F4A7C15ull;
+    uint32_t level_rng_ = 1u;   // minstd_rand0 state, default seed (std::default_random_engine, index.hpp:2082)
+    size_t build_batch_ = 0;    // max nodes inserted per batch; 0 = one per resident CTA; 1 = the reference's sequential order
+    size_t build_ratio_ = 64;   // a batch never exceeds (visible nodes) / build_ratio_
+    double last_build_ms_ = 0;
+    uint64_t last_build_dist_ = 0;
 
     // device arrays
     uint8_t* d_vectors_ = nullptr;
@@ -132,6 +137,7 @@ class Index {
     void* h_pinned_ = nullptr;
     size_t pinned_bytes_ = 0;
     SearchStats last_stats_{};
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     uint32_t last_nq_ = 0;
     std::mutex mu_;
 

@@ -1,0 +1,458 @@
+// lantern_b200 -- the graph walker shared by the search and build kernels.
+//
+// One CTA (4 warps) executes, for one "value" (a query or a vector being inserted), the reference's
+//   search_for_one_            U/include/usearch/index.hpp:3277-3316   -> Walker::greedy
+//   search_to_find_in_base_    :3400-3485                              -> Walker::beam(level 0)
+//   search_to_insert_          :3324-3392                              -> Walker::beam(level l)
+//   refine_                    :3515-3561                              -> Walker::refine
+// with the same decision sequence (stored neighbour order, strict '<', insert-before-equal, evict-last).
+// The candidate queue (`next`, a max-heap on -distance in the reference) is represented by "unexpanded"
+// flags on the sorted `top` list: an element evicted from `top` has distance >= radius and can never be
+// popped before the stop test (:3445 / :3351) fires, so both formulations expand the same nodes; they can
+// differ only for exact distance ties.
+//
+// Data movement: neighbour rows travel HBM -> shared memory as 1-D bulk async copies (TMA engine,
+// `cp.async.bulk`, mbarrier complete_tx).  Candidate j of a batch is served by warp j%4, which owns the
+// ring slots {warp, warp+4, ...} and refills a slot itself right after reading it, so a warp's pipeline
+// needs no cross-warp synchronisation.  Distances are reduced with warp shuffles (distance.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "distance.cuh"
+#include "engine.h"
+
+namespace lb200 {
+
+constexpr int kWalkThreads = 128;
+constexpr int kWalkWarps = kWalkThreads / 32;
+constexpr uint32_t kDone = 0xFFFFFFFFu;
+constexpr uint32_t kIdMask = 0x7FFFFFFFu;
+
+struct WalkCtrl {
+    uint32_t item;     // current work item (query / node / segment)
+    uint32_t n;        // candidates in cand_id[], or kDone
+    uint32_t ntouched; // entries in the touched list
+    uint32_t top_size; // size of the top list after a beam
+};
+
+struct WalkSmem {
+    uint8_t* ring;
+    uint64_t* full;
+    float* top_d;
+    uint32_t* top_i;
+    uint32_t* cand_id;
+    float* cand_d;
+    WalkCtrl* ctrl;
+};
+
+struct WalkLayout {
+    size_t full, top_d, top_i, cand_id, cand_d, ctrl, total;
+};
+
+// R ring slots of row_bytes, a top list of `top_cap` entries, candidate arrays of `cand_cap` entries.
+__host__ __device__ inline WalkLayout walk_layout(uint32_t R, uint32_t row_bytes, uint32_t top_cap, uint32_t cand_cap) {
+    WalkLayout l;
+    size_t o = (size_t)R * row_bytes;
+    o = (o + 15) & ~(size_t)15;
+    l.full = o, o += (size_t)R * 8;
+    l.top_d = o, o += (size_t)top_cap * 4;
+    l.top_i = o, o += (size_t)top_cap * 4;
+    l.cand_id = o, o += (size_t)cand_cap * 4;
+    l.cand_d = o, o += (size_t)cand_cap * 4;
+    o = (o + 15) & ~(size_t)15;
+    l.ctrl = o, o += sizeof(WalkCtrl);
+    l.total = o;
+    return l;
+}
+
+inline uint32_t pick_ring_slots(uint32_t row_bytes) {
+    uint32_t r = (48u * 1024u / row_bytes) & ~3u;
+    if (r < 4)
+        r = 4;
+    if (r > 32)
+        r = 32;
+    return r;
+}
+
+inline int pick_nq(uint32_t row_bytes) {
+    const uint32_t need = (row_bytes / 16 + 31) / 32;
+    const int opts[] = {1, 2, 3, 4, 6, 8, 12, 16};
+    for (int o : opts)
+        if ((uint32_t)o >= need)
+            return o;
+    return -1;
+}
+
+// Warp-cooperative sorted insert == sorted_buffer_gt::insert (index.hpp:752-763): position = lower_bound
+// (new element goes BEFORE equal ones), tail evicted when the list is full.
+// Precondition (index.hpp:3470): size < L || d < top_d[size-1].
+__device__ __forceinline__ void top_insert(float* td, uint32_t* ti, uint32_t& size, uint32_t& cursor, uint32_t L, float d,
+                                           uint32_t id, int lane) {
+    uint32_t pos = 0;
+    for (uint32_t b = 0; b < size; b += 32) {
+        uint32_t e = b + lane;
+        bool less = e < size && td[e] < d;
+        pos += __popc(__ballot_sync(0xffffffffu, less));
+    }
+    const uint32_t last = (size == L) ? L - 1 : size;
+    for (int hi = (int)last; hi > (int)pos; hi -= 32) {
+        int idx = hi - lane;
+        bool act = idx > (int)pos;
+        float vd = 0.f;
+        uint32_t vi = 0;
+        if (act)
+            vd = td[idx - 1], vi = ti[idx - 1];
+        __syncwarp();
+        if (act)
+            td[idx] = vd, ti[idx] = vi;
+        __syncwarp();
+    }
+    if (lane == 0)
+        td[pos] = d, ti[pos] = id;
+    __syncwarp();
+    size = last + 1;
+    if (pos <= cursor)
+        cursor = pos;
+}
+
+template <int DM, int SK, int NQ> struct Walker {
+    GraphView g;
+    WalkSmem sm;
+    uint32_t* vis;
+    uint32_t* touched;
+    uint32_t touched_cap;
+    size_t words_per_cta;
+    uint4 qreg[NQ];
+    float a2;
+    uint32_t phase_bits;
+    uint32_t nchunks, R, SPW;
+    int warp, lane;
+    unsigned long long st_dist, st_pops, st_hops; // thread 0's copy is the one that is reported
+
+    __device__ __forceinline__ void init(const GraphView& gv, uint8_t* smem_raw, const WalkLayout& lay, uint32_t ring_slots,
+                                         const SearchScratch& s) {
+        g = gv;
+        sm.ring = smem_raw;
+        sm.full = reinterpret_cast<uint64_t*>(smem_raw + lay.full);
+        sm.top_d = reinterpret_cast<float*>(smem_raw + lay.top_d);
+        sm.top_i = reinterpret_cast<uint32_t*>(smem_raw + lay.top_i);
+        sm.cand_id = reinterpret_cast<uint32_t*>(smem_raw + lay.cand_id);
+        sm.cand_d = reinterpret_cast<float*>(smem_raw + lay.cand_d);
+        sm.ctrl = reinterpret_cast<WalkCtrl*>(smem_raw + lay.ctrl);
+        warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        nchunks = g.row_bytes / 16;
+        R = ring_slots, SPW = ring_slots / kWalkWarps;
+        phase_bits = 0;
+        a2 = 0.f;
+        st_dist = st_pops = st_hops = 0;
+        vis = s.visited + (size_t)blockIdx.x * s.words_per_cta;
+        touched = s.touched + (size_t)blockIdx.x * s.touched_cap;
+        touched_cap = s.touched_cap;
+        words_per_cta = s.words_per_cta;
+        if (threadIdx.x == 0) {
+            for (uint32_t i = 0; i < R; ++i)
+                mbar_init(&sm.full[i], 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+    }
+
+    // value -> registers; every warp keeps its own copy.  `row` points to a 16-byte padded row in global memory.
+    __device__ __forceinline__ void load_value(const uint8_t* row) {
+        const uint4* qg = reinterpret_cast<const uint4*>(row);
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            uint32_t c = lane + 32 * i;
+            qreg[i] = c < nchunks ? __ldg(qg + c) : make_uint4(0, 0, 0, 0);
+            part += query_norm_chunk<DM, SK>(qreg[i]);
+        }
+        if constexpr (DM == DM_COS)
+            a2 = warp_sum(part);
+    }
+
+    __device__ __forceinline__ void issue(uint32_t slot, uint32_t id) {
+        uint64_t* bar = &sm.full[slot];
+        mbar_arrive_expect_tx(bar, g.row_bytes);
+        bulk_g2s(sm.ring + (size_t)slot * g.row_bytes, g.vectors + (size_t)id * g.row_bytes, g.row_bytes, bar);
+    }
+
+    // distances value -> cand_id[0..n) into cand_d[0..n).  Callers bracket it with __syncthreads().
+    __device__ __forceinline__ void eval(uint32_t n) {
+        const uint32_t T = n > (uint32_t)warp ? (n - warp + kWalkWarps - 1) / kWalkWarps : 0;
+        if ((uint32_t)lane < min(T, SPW))
+            issue(warp + kWalkWarps * lane, sm.cand_id[warp + kWalkWarps * lane]);
+        uint32_t si = 0;
+        for (uint32_t t = 0; t < T; ++t) {
+            const uint32_t slot = warp + kWalkWarps * si;
+            mbar_wait(&sm.full[slot], (phase_bits >> si) & 1u);
+            phase_bits ^= 1u << si;
+            const uint4* row = reinterpret_cast<const uint4*>(sm.ring + (size_t)slot * g.row_bytes);
+            DistAcc<DM, SK> acc;
+            acc.reset();
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                uint32_t c = lane + 32 * i;
+                if (c < nchunks) {
+                    uint4 r = row[c];
+                    accum_chunk<DM, SK>(acc, qreg[i], r);
+                }
+            }
+            float d = finish_distance<DM, SK>(acc, a2);
+            if (lane == 0)
+                sm.cand_d[warp + kWalkWarps * t] = d;
+            __syncwarp();
+            if (t + SPW < T && lane == 0) {
+                fence_proxy_async(); // our generic-proxy reads of the slot precede the async refill
+                issue(slot, sm.cand_id[warp + kWalkWarps * (t + SPW)]);
+            }
+            si = (si + 1 == SPW) ? 0 : si + 1;
+        }
+    }
+
+    __device__ __forceinline__ const uint32_t* list_of(uint32_t node, int level, uint32_t& width) const {
+        if (level == 0) {
+            width = g.M0;
+            return g.adj0 + (size_t)node * g.M0;
+        }
+        width = g.M;
+        return g.upper_adj + ((size_t)__ldg(g.upper_ref + node) + (level - 1)) * g.M;
+    }
+
+    // distance value -> one node (entry point)
+    __device__ __forceinline__ float measure_one(uint32_t id) {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            sm.cand_id[0] = id;
+        __syncthreads();
+        eval(1);
+        __syncthreads();
+        st_dist += 1;
+        return sm.cand_d[0];
+    }
+
+    // search_for_one_: levels from_level, from_level-1, ..., stop_level+1
+    __device__ __forceinline__ void greedy(uint32_t& cur, float& cur_d, int from_level, int stop_level) {
+        for (int level = from_level; level > stop_level; --level) {
+            for (;;) {
+                __syncthreads(); // everyone is done with cand_* of the previous pass
+                if (warp == 0) {
+                    uint32_t width;
+                    const uint32_t* list = list_of(cur, level, width);
+                    uint32_t n = 0;
+                    for (uint32_t off = 0; off < width; off += 32) {
+                        uint32_t id = (off + lane < width) ? __ldg(list + off + lane) : kNoNeighbor;
+                        bool valid = id != kNoNeighbor;
+                        uint32_t m = __ballot_sync(0xffffffffu, valid);
+                        if (valid)
+                            sm.cand_id[n + __popc(m & ((1u << lane) - 1u))] = id;
+                        n += __popc(m);
+                    }
+                    if (lane == 0)
+                        sm.ctrl->n = n;
+                }
+                __syncthreads();
+                const uint32_t n = sm.ctrl->n;
+                eval(n);
+                __syncthreads();
+                // one pass of index.hpp:3304-3311: chain of strict improvements == first minimum below cur_d
+                float best = cur_d;
+                int bi = -1;
+                for (uint32_t j = 0; j < n; ++j) {
+                    float d = sm.cand_d[j];
+                    if (d < best)
+                        best = d, bi = (int)j;
+                }
+                st_dist += n, st_hops += 1;
+                if (bi < 0)
+                    break;
+                cur = sm.cand_id[bi], cur_d = best;
+            }
+        }
+    }
+
+    // Beam search on one level with top list capacity L, starting from `start` (distance start_d already known:
+    // the reference re-measures it, so the counter advances).  `skip` = node whose expansion is skipped
+    // (index.hpp:3357 new_slot; kNoNeighbor for plain search).  Leaves the ascending top list in shared memory;
+    // returns its size (uniform across the CTA).  Visited bits are cleared before returning.
+    __device__ __forceinline__ uint32_t beam(int level, uint32_t start, float start_d, uint32_t L, uint32_t skip) {
+        uint32_t size = 0, cursor = 0, ntouched = 0; // warp-0 uniform
+        __syncthreads();
+        if (warp == 0) {
+            if (lane == 0) {
+                sm.top_d[0] = start_d, sm.top_i[0] = start;
+                atomicOr(&vis[start >> 5], 1u << (start & 31));
+                touched[0] = start >> 5;
+            }
+            size = 1, cursor = 0, ntouched = 1;
+            st_dist += 1; // index.hpp:3436 / :3343
+            __syncwarp();
+        }
+        for (;;) {
+            __syncthreads(); // (A) insertions of the previous round are complete
+            if (warp == 0) {
+                if (cursor >= size) {
+                    if (lane == 0)
+                        sm.ctrl->n = kDone;
+                } else {
+                    const uint32_t c = sm.top_i[cursor];
+                    __syncwarp();
+                    if (lane == 0)
+                        sm.top_i[cursor] = c | kExpandedBit;
+                    __syncwarp();
+                    { // advance the cursor to the next unexpanded entry
+                        uint32_t nxt = size;
+                        for (uint32_t b = cursor + 1; b < size; b += 32) {
+                            uint32_t e = b + lane;
+                            bool un = e < size && !(sm.top_i[e] & kExpandedBit);
+                            uint32_t m = __ballot_sync(0xffffffffu, un);
+                            if (m) {
+                                nxt = b + __ffs(m) - 1;
+                                break;
+                            }
+                        }
+                        cursor = nxt;
+                    }
+                    uint32_t n = 0;
+                    if (c != skip) {
+                        uint32_t width;
+                        const uint32_t* list = list_of(c, level, width);
+                        for (uint32_t off = 0; off < width; off += 32) {
+                            uint32_t id = (off + lane < width) ? __ldg(list + off + lane) : kNoNeighbor;
+                            bool valid = id != kNoNeighbor;
+                            if (!__any_sync(0xffffffffu, valid))
+                                break;
+                            // duplicate ids inside one list are legal in reference graphs (refine_ padding,
+                            // index.hpp:3554-3558): only the first occurrence can be "unseen"
+                            uint32_t peers = __match_any_sync(0xffffffffu, id);
+                            bool first = valid && ((uint32_t)(__ffs(peers) - 1) == (uint32_t)lane);
+                            bool fresh = false;
+                            if (first) {
+                                uint32_t bit = 1u << (id & 31);
+                                fresh = !(atomicOr(&vis[id >> 5], bit) & bit);
+                            }
+                            uint32_t m = __ballot_sync(0xffffffffu, fresh);
+                            uint32_t rank = __popc(m & ((1u << lane) - 1u));
+                            if (fresh) {
+                                sm.cand_id[n + rank] = id;
+                                if (ntouched + rank < touched_cap)
+                                    touched[ntouched + rank] = id >> 5;
+                                if (level == 0)
+                                    prefetch_l2(g.adj0 + (size_t)id * g.M0); // its adjacency line, for when it is popped
+                            }
+                            n += __popc(m);
+                            ntouched += __popc(m);
+                        }
+                        st_pops += 1;
+                    }
+                    if (lane == 0)
+                        sm.ctrl->n = n;
+                }
+            }
+            __syncthreads(); // (B)
+            const uint32_t n = sm.ctrl->n;
+            if (n == kDone)
+                break;
+            eval(n);
+            __syncthreads(); // (C)
+            if (warp == 0) {
+                st_dist += n;
+                for (uint32_t j = 0; j < n; ++j) {
+                    const float d = sm.cand_d[j];
+                    // index.hpp:3470 / :3382: top.size() < top_limit || successor_dist < radius
+                    if (size < L || d < sm.top_d[size - 1])
+                        top_insert(sm.top_d, sm.top_i, size, cursor, L, d, sm.cand_id[j], lane);
+                }
+            }
+        }
+        if (threadIdx.x == 0)
+            sm.ctrl->ntouched = ntouched, sm.ctrl->top_size = size;
+        __syncthreads();
+        { // un-visit only the words this walk touched
+            const uint32_t nt = sm.ctrl->ntouched;
+            if (nt <= touched_cap) {
+                for (uint32_t i = threadIdx.x; i < nt; i += kWalkThreads)
+                    vis[touched[i]] = 0u;
+            } else {
+                for (size_t i = threadIdx.x; i < words_per_cta; i += kWalkThreads)
+                    vis[i] = 0u;
+            }
+        }
+        const uint32_t out = sm.ctrl->top_size;
+        __syncthreads(); // bitmap is clean and ctrl may be reused
+        return out;
+    }
+
+    // refine_ (index.hpp:3515-3561) on the ascending list top_d/top_i[0..count): keeps the closest element, then
+    // accepts a candidate only if it is not closer to an accepted element than to the centre; because
+    // skip_pruned_connections == false (index.hpp:1245) the accepted prefix is followed by whatever sits at
+    // positions [accepted, needed) -- stale entries, possibly duplicates.  Destroys the value registers.
+    // Returns the size of the resulting view (uniform across the CTA).
+    __device__ __forceinline__ uint32_t refine(uint32_t count, uint32_t needed) {
+        if (count < needed)
+            return count;
+        uint32_t submitted = 1, consumed = 1;
+        while (submitted < needed && consumed < count) {
+            __syncthreads();
+            const uint32_t c_id = sm.top_i[consumed] & kIdMask;
+            const float c_d = sm.top_d[consumed];
+            load_value(g.vectors + (size_t)c_id * g.row_bytes);
+            for (uint32_t j = threadIdx.x; j < submitted; j += kWalkThreads)
+                sm.cand_id[j] = sm.top_i[j] & kIdMask;
+            __syncthreads();
+            eval(submitted);
+            __syncthreads();
+            bool good = true;
+            for (uint32_t j = 0; j < submitted; ++j)
+                if (sm.cand_d[j] < c_d) { // index.hpp:3536
+                    good = false;
+                    break;
+                }
+            st_dist += submitted;
+            if (good) {
+                if (threadIdx.x == 0)
+                    sm.top_d[submitted] = c_d, sm.top_i[submitted] = sm.top_i[consumed];
+                submitted++;
+            }
+            consumed++;
+        }
+        __syncthreads();
+        return needed; // count >= needed, so shrink(max(submitted, needed)) == needed
+    }
+};
+
+// ---- (DM, SK, NQ) dispatch shared by the launchers ----------------------------------------------------
+template <typename Fn> void dispatch_walk(int dm, int sk, int nq, Fn&& fn) {
+#define LB_NQ_CASES(DMv, SKv)                                                                                          \
+    switch (nq) {                                                                                                      \
+    case 1: fn(std::integral_constant<int, DMv>{}, std::integral_constant<int, SKv>{}, std::integral_constant<int, 1>{}); return;   \
+    case 2: fn(std::integral_constant<int, DMv>{}, std::integral_constant<int, SKv>{}, std::integral_constant<int, 2>{}); return;   \
+    case 3: fn(std::integral_constant<int, DMv>{}, std::integral_constant<int, SKv>{}, std::integral_constant<int, 3>{}); return;   \
+    case 4: fn(std::integral_constant<int, DMv>{}, std::integral_constant<int, SKv>{}, std::integral_constant<int, 4>{}); return;   \
+    case 6: fn(std::integral_constant<int, DMv>{}, std::integral_constant<int, SKv>{}, std::integral_constant<int, 6>{}); return;   \
+    case 8: fn(std::integral_constant<int, DMv>{}, std::integral_constant<int, SKv>{}, std::integral_constant<int, 8>{}); return;   \
+    case 12: fn(std::integral_constant<int, DMv>{}, std::integral_constant<int, SKv>{}, std::integral_constant<int, 12>{}); return; \
+    case 16: fn(std::integral_constant<int, DMv>{}, std::integral_constant<int, SKv>{}, std::integral_constant<int, 16>{}); return; \
+    default: break;                                                                                                    \
+    }
+    if (dm == DM_L2SQ && sk == SK_F32) {
+        LB_NQ_CASES(DM_L2SQ, SK_F32)
+    } else if (dm == DM_COS && sk == SK_F32) {
+        LB_NQ_CASES(DM_COS, SK_F32)
+    } else if (dm == DM_L2SQ && sk == SK_F16) {
+        LB_NQ_CASES(DM_L2SQ, SK_F16)
+    } else if (dm == DM_COS && sk == SK_F16) {
+        LB_NQ_CASES(DM_COS, SK_F16)
+    } else if (dm == DM_L2SQ && sk == SK_I8) {
+        LB_NQ_CASES(DM_L2SQ, SK_I8)
+    } else if (dm == DM_COS && sk == SK_I8) {
+        LB_NQ_CASES(DM_COS, SK_I8)
+    } else if (dm == DM_HAMMING && sk == SK_B1) {
+        LB_NQ_CASES(DM_HAMMING, SK_B1)
+    }
+#undef LB_NQ_CASES
+    throw CudaError("unsupported metric / scalar kind / dimensionality combination");
+}
+
+} // namespace lb200
