@@ -19,7 +19,7 @@ The graph is built by the engine itself on the GPU (lb200_add_batch_device + lb2
            which also yields the full-size same-graph id parity reported under `parity`.
 --impl reference: the reference alone on the host cores: builds its own graph over a bounded prefix of the corpus
            (sized for ~1 minute of multi-threaded adds) and searches the same query batches.
-Every step uses a fresh batch of queries; the corpus (3 GB) is far larger than L2 (126 MB).
+Steps cycle through a pool of distinct query batches; the corpus (3 GB), gathered at random, is far larger than L2 (126 MB).
 """
 import argparse
 import json
@@ -91,7 +91,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -151,35 +151,48 @@ def run_reference(args, wl):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liboracle_usearch.so missing (run oracle/Makefile)"}))
         return
     cores = reflib.lib().refx_hardware_threads()
-    # bounded sample: a prefix of the corpus the reference can index in about a minute with all cores
-    n_ref = int(min(wl["n"], max(20_000, 350 * cores * 60)))
-    if args.ref_rows:
-        n_ref = min(wl["n"], args.ref_rows)
-    X = structured_np(n_ref, wl["dim"], SEED_CORPUS)
+    # bounded sample: a prefix of the corpus the reference can index in about `--ref-build-seconds` with all cores;
+    # the rate is measured on a pilot of 20k rows (it only falls slowly, ~log N, afterwards)
+    pilot = min(wl["n"], 20_000)
+    X = structured_np(wl["n"] if args.ref_rows == 0 else min(wl["n"], args.ref_rows), wl["dim"], SEED_CORPUS)
     nsteps = args.steps + args.warmup
-    Q = structured_np(nsteps * wl["batch"], wl["dim"], SEED_QUERY)
+    pool = min(nsteps, args.query_pool)
+    Q = structured_np(pool * wl["batch"], wl["dim"], SEED_QUERY)
     idx = reflib.RefIndex(wl["dim"], wl["metric"], M=wl["M"], efc=wl["efc"], ef=wl["ef"], threads=cores)
-    idx.reserve(n_ref)
+    idx.reserve(len(X))
+    keys = np.arange(1, len(X) + 1, dtype=np.uint64)
     t0 = time.perf_counter()
-    idx.add_batch(np.arange(1, n_ref + 1, dtype=np.uint64), X, threads=cores)
+    idx.add_batch(keys[:pilot], X[:pilot], threads=cores)
+    t_pilot = time.perf_counter() - t0
+    n_ref = len(X)
+    if not args.ref_rows:
+        n_ref = int(min(len(X), max(pilot, 0.7 * (pilot / t_pilot) * args.ref_build_seconds)))
+    if n_ref > pilot:
+        idx.add_batch(keys[pilot:n_ref], X[pilot:n_ref], threads=cores)
     t_build = time.perf_counter() - t0
+    # each timed step is a bounded sample of the batch, sized from the warm-up rate so that K steps take about a minute
+    B = wl["batch"]
+    t0 = time.perf_counter()
+    for s in range(args.warmup):
+        idx.search_batch(Q[(s % pool) * B:((s % pool) + 1) * B], wl["k"], threads=cores)
+    qps_est = args.warmup * B / (time.perf_counter() - t0)
+    per_step = int(max(min(B, 64), min(B, args.ref_seconds * qps_est / max(1, args.steps))))
     times = []
-    for s in range(nsteps):
-        q = Q[s * wl["batch"]:(s + 1) * wl["batch"]]
+    for s in range(args.steps):
+        q = Q[(s % pool) * B:(s % pool) * B + per_step]
         t0 = time.perf_counter()
         keys, dists, counts, comp, vis = idx.search_batch(q, wl["k"], threads=cores)
-        dt = time.perf_counter() - t0
-        if s >= args.warmup:
-            times.append(dt)
+        times.append(time.perf_counter() - t0)
     total = sum(times)
-    value = args.steps * wl["batch"] / total
-    sample = "reference builds its own graph over the first %d of %d corpus rows (%.0f s, %d threads); %d batches of %d queries" % (
-        n_ref, wl["n"], t_build, cores, args.steps, wl["batch"])
+    value = args.steps * per_step / total
+    sample = ("reference builds its own graph over the first %d of %d corpus rows (%.0f s, %d threads); each step = the first %d "
+              "queries of a %d-query batch" % (n_ref, wl["n"], t_build, cores, per_step, B))
     line = {
         "impl": "reference", "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "corpus_rows_indexed": n_ref, "ef": wl["ef"], "k": wl["k"], "batch": wl["batch"]},
+        "config": {"workload": wl["desc"], "corpus_rows_indexed": n_ref, "ef": wl["ef"], "k": wl["k"], "batch": wl["batch"],
+                   "queries_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "build_vectors_per_s": n_ref / t_build,
@@ -206,12 +219,13 @@ def run_ours(args, wl):
     n, dim, k, ef, B = wl["n"], wl["dim"], wl["k"], wl["ef"], wl["batch"]
     nsteps = args.steps + args.warmup
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    pool = min(nsteps, args.query_pool)  # distinct query batches, cycled: step s uses batch s % pool
 
     # ---- corpus shard of this rank: contiguous row range ----
     lo, hi = (n * rank) // world, (n * (rank + 1)) // world
     t0 = time.perf_counter()
     X = structured_torch(n, dim, SEED_CORPUS, dev)[lo:hi].contiguous() if world > 1 else structured_torch(n, dim, SEED_CORPUS, dev)
-    Q = structured_torch(nsteps * B, dim, SEED_QUERY, dev)
+    Q = structured_torch(pool * B, dim, SEED_QUERY, dev)
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t0
 
@@ -236,7 +250,7 @@ def run_ours(args, wl):
         m_dists = torch.empty((B, k), dtype=torch.float32, device=dev)
 
     def step_device(s):
-        q = Q[s * B:(s + 1) * B]
+        q = Q[(s % pool) * B:((s % pool) + 1) * B]
         idx.search_batch_device(q.data_ptr(), B, dim * 4, "f32", k, ef_shard, out_keys.data_ptr(), out_dists.data_ptr(),
                                 out_counts.data_ptr(), stream.cuda_stream)
         if world > 1:  # the one exchange step: all-gather of per-shard top-k over NVLink, then a G-way merge
@@ -303,7 +317,7 @@ def run_ours(args, wl):
     # ---- roofline of the search kernel: separate pass with per-step counters (the stats call synchronises) ----
     alg_bytes, kern_ms, n_dist, pops = 0, 0.0, 0, 0
     for s in range(args.warmup, nsteps):
-        q = Q[s * B:(s + 1) * B]
+        q = Q[(s % pool) * B:((s % pool) + 1) * B]
         idx.search_batch_device(q.data_ptr(), B, dim * 4, "f32", k, ef_shard, out_keys.data_ptr(), out_dists.data_ptr(),
                                 out_counts.data_ptr(), stream.cuda_stream)
         st = idx.last_stats()
@@ -326,17 +340,17 @@ def run_ours(args, wl):
     # ---- e2e through the reference-facing host call: pinned host buffers in/out, copies inside the timed region ----
     e2e = None
     if world == 1:
-        hq = torch.empty((nsteps * B, dim), dtype=torch.float32).pin_memory()
+        hq = torch.empty((pool * B, dim), dtype=torch.float32).pin_memory()
         hq.copy_(Q)
         hk = torch.empty((B, k), dtype=torch.int64).pin_memory()
         hd = torch.empty((B, k), dtype=torch.float32).pin_memory()
         hc = torch.empty((B,), dtype=torch.int64).pin_memory()
         for s in range(args.warmup):
-            idx.search_batch_raw(hq[s * B].data_ptr(), B, dim * 4, "f32", k, ef, hk.data_ptr(), hd.data_ptr(), hc.data_ptr())
+            idx.search_batch_raw(hq[(s % pool) * B].data_ptr(), B, dim * 4, "f32", k, ef, hk.data_ptr(), hd.data_ptr(), hc.data_ptr())
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for s in range(args.warmup, nsteps):
-            idx.search_batch_raw(hq[s * B].data_ptr(), B, dim * 4, "f32", k, ef, hk.data_ptr(), hd.data_ptr(), hc.data_ptr())
+            idx.search_batch_raw(hq[(s % pool) * B].data_ptr(), B, dim * 4, "f32", k, ef, hk.data_ptr(), hd.data_ptr(), hc.data_ptr())
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         e2e = {"value": args.steps * B / dt, "unit": "queries/s", "h2d_bytes_per_step": B * dim * 4,
@@ -355,10 +369,10 @@ def run_ours(args, wl):
             t_load = time.perf_counter() - t0
             del buf
             ridx._loaded = None
-            qh = Q[:nsteps * B].cpu().numpy()
+            qh = Q.cpu().numpy()
             spent, done, first = 0.0, 0, None
             s = 0
-            while spent < args.cpu_seconds and s < nsteps:
+            while spent < args.cpu_seconds and s < pool:
                 qb = qh[s * B:(s + 1) * B]
                 t0 = time.perf_counter()
                 rkeys, rd, rc, comp, vis = ridx.search_batch(qb, k, threads=cores)
@@ -393,7 +407,7 @@ def run_ours(args, wl):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "corpus_rows": n, "rows_per_gpu": hi - lo, "ef": ef, "ef_per_shard": ef_shard, "k": k,
                        "batch": B, "parallelism": "row-range shards x%d + NCCL all-gather of top-k + merge" % world if world > 1 else "1 GPU",
-                       "l2_policy": "inputs larger than L2: fresh query batch every step over a %.1f GB corpus" % ((hi - lo) * dim * 4 / 1e9),
+                       "l2_policy": "inputs larger than L2: %.1f GB corpus gathered at random; %d distinct query batches cycled" % ((hi - lo) * dim * 4 / 1e9, pool),
                        "generator": "x = z P + %.2f eps, z~N(0,I_%d), seeds %d/%d/%d" % (NOISE, LATENT, SEED_P, SEED_CORPUS, SEED_QUERY)},
             "recall_at_10": rec, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "parity": parity,
@@ -407,13 +421,16 @@ def run_ours(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--query-pool", type=int, default=32, help="distinct query batches (cycled over the steps)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("LB200_WORKLOAD", "cfg2"), choices=sorted(WORKLOADS))
     ap.add_argument("--shard-ef", type=int, default=0, help="per-shard ef when --gpus > 1 (0 = the workload's ef)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="bound on the cpu_baseline search time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-seconds", type=float, default=60.0, help="--impl reference: target duration of the K timed steps")
+    ap.add_argument("--ref-build-seconds", type=float, default=75.0, help="--impl reference: budget for the reference's own build")
     ap.add_argument("--ref-rows", type=int, default=0, help="--impl reference: corpus prefix to index (0 = auto by core count)")
     ap.add_argument("--per-step-stats", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

@@ -5,6 +5,7 @@
 // pick expansion = max(ef, k), run the search, dump keys+distances), for whole batches.
 #include "engine.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -219,6 +220,9 @@ GraphView Index::view() const {
     g.dims = (uint32_t)cfg_.dims;
     g.num_centroids = (uint32_t)cfg_.num_centroids;
     g.num_subvectors = (uint32_t)cfg_.num_subvectors;
+    g.flags = 2u; // measured best on B200: L2-prefetch the adjacency line of nodes that enter the top list
+    if (const char* e = getenv("LB200_FLAGS"))
+        g.flags = (uint32_t)atoi(e);
     return g;
 }
 

@@ -52,6 +52,7 @@ struct GraphView {
     int32_t max_level;
     // PQ (row_bytes then is the padded code width)
     const float* codebook; // [num_centroids][dims]
+    uint32_t flags;        // tuning: 1 = prefetch adjacency of every measured node, 2 = of accepted nodes only, 4 = evict-first rows
     uint32_t dims, num_centroids, num_subvectors;
 };
 

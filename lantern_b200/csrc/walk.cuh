@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "distance.cuh"
 #include "engine.h"
@@ -67,7 +68,10 @@ __host__ __device__ inline WalkLayout walk_layout(uint32_t R, uint32_t row_bytes
 }
 
 inline uint32_t pick_ring_slots(uint32_t row_bytes) {
-    uint32_t r = (48u * 1024u / row_bytes) & ~3u;
+    uint32_t budget = 24u * 1024u; // 8 slots of a d=768 f32 row: 8 CTAs/SM; measured best on B200 (profiles/)
+    if (const char* e = getenv("LB200_RING_BYTES")) // tuning knob (bytes of row staging per CTA)
+        budget = (uint32_t)atoi(e);
+    uint32_t r = (budget / row_bytes) & ~3u;
     if (r < 4)
         r = 4;
     if (r > 32)
@@ -126,6 +130,7 @@ template <int DM, int SK, int NQ> struct Walker {
     uint4 qreg[NQ];
     float a2;
     uint32_t phase_bits;
+    uint64_t pol;
     uint32_t nchunks, R, SPW;
     int warp, lane;
     unsigned long long st_dist, st_pops, st_hops; // thread 0's copy is the one that is reported
@@ -144,6 +149,7 @@ template <int DM, int SK, int NQ> struct Walker {
         nchunks = g.row_bytes / 16;
         R = ring_slots, SPW = ring_slots / kWalkWarps;
         phase_bits = 0;
+        pol = policy_evict_first();
         a2 = 0.f;
         st_dist = st_pops = st_hops = 0;
         vis = s.visited + (size_t)blockIdx.x * s.words_per_cta;
@@ -175,7 +181,10 @@ template <int DM, int SK, int NQ> struct Walker {
     __device__ __forceinline__ void issue(uint32_t slot, uint32_t id) {
         uint64_t* bar = &sm.full[slot];
         mbar_arrive_expect_tx(bar, g.row_bytes);
-        bulk_g2s(sm.ring + (size_t)slot * g.row_bytes, g.vectors + (size_t)id * g.row_bytes, g.row_bytes, bar);
+        if (g.flags & 4u)
+            bulk_g2s_hint(sm.ring + (size_t)slot * g.row_bytes, g.vectors + (size_t)id * g.row_bytes, g.row_bytes, bar, pol);
+        else
+            bulk_g2s(sm.ring + (size_t)slot * g.row_bytes, g.vectors + (size_t)id * g.row_bytes, g.row_bytes, bar);
     }
 
     // distances value -> cand_id[0..n) into cand_d[0..n).  Callers bracket it with __syncthreads().
@@ -338,7 +347,7 @@ template <int DM, int SK, int NQ> struct Walker {
                                 sm.cand_id[n + rank] = id;
                                 if (ntouched + rank < touched_cap)
                                     touched[ntouched + rank] = id >> 5;
-                                if (level == 0)
+                                if (level == 0 && (g.flags & 1u))
                                     prefetch_l2(g.adj0 + (size_t)id * g.M0); // its adjacency line, for when it is popped
                             }
                             n += __popc(m);
@@ -358,11 +367,24 @@ template <int DM, int SK, int NQ> struct Walker {
             __syncthreads(); // (C)
             if (warp == 0) {
                 st_dist += n;
-                for (uint32_t j = 0; j < n; ++j) {
-                    const float d = sm.cand_d[j];
-                    // index.hpp:3470 / :3382: top.size() < top_limit || successor_dist < radius
-                    if (size < L || d < sm.top_d[size - 1])
-                        top_insert(sm.top_d, sm.top_i, size, cursor, L, d, sm.cand_id[j], lane);
+                // index.hpp:3470 / :3382: accepted iff top.size() < top_limit || successor_dist < radius.  The radius only
+                // shrinks once the list is full, so a candidate that fails against the CURRENT radius can never pass
+                // later in this round: filter those out in parallel, then replay the survivors in stored order.
+                for (uint32_t base = 0; base < n; base += 32) {
+                    const uint32_t j = base + lane;
+                    const float dj = j < n ? sm.cand_d[j] : INFINITY;
+                    uint32_t m = __ballot_sync(0xffffffffu, j < n && (size < L || dj < sm.top_d[size - 1]));
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float d = __shfl_sync(0xffffffffu, dj, b);
+                        if (size < L || d < sm.top_d[size - 1]) {
+                            const uint32_t id = sm.cand_id[base + b];
+                            top_insert(sm.top_d, sm.top_i, size, cursor, L, d, id, lane);
+                            if (level == 0 && (g.flags & 2u) && lane == 0)
+                                prefetch_l2(g.adj0 + (size_t)id * g.M0);
+                        }
+                    }
                 }
             }
         }
