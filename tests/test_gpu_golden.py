@@ -1,0 +1,156 @@
+"""GPU parity against the committed golden fixtures (outputs of the unmodified reference) and the oracle, through
+the C ABI: stateless kernels (distance, cast, PQ codec, exact search, shard merge) and index round trips."""
+import os
+
+import numpy as np
+import pytest
+
+from test_golden import CUBE, LATTICE, PQ_CODEBOOK, G, int_bits, same_up_to_ties
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_index(eng, X, metric, quant="f32", keys=None, sequential=True, **kw):
+    dim = X.shape[1] * 8 if X.dtype == np.uint8 else X.shape[1]
+    g = eng.Index(dim, metric, quant, **kw)
+    if sequential:
+        g.set_option("build_batch", 1)  # the reference's insertion order
+    g.reserve(len(X))
+    g.add_batch(np.arange(len(X), dtype=np.uint64) if keys is None else keys.astype(np.uint64), X)
+    g.build()
+    return g
+
+
+@pytest.mark.parametrize("metric", ["l2sq", "cos", "hamming"])
+def test_cube_reference_outputs(eng, metric):
+    X = int_bits(CUBE) if metric == "hamming" else CUBE
+    g = gpu_index(eng, X, metric, "b1" if metric == "hamming" else "f32", keys=100 + np.arange(8), M=2, efc=128, ef=4)
+    k, d, c = g.search_batch(X, 8)
+    same_up_to_ties(k, d, G["cube_%s_keys" % metric], G["cube_%s_dists" % metric])
+    if metric != "hamming":
+        assert np.array_equal(g.save_buffer(), G["cube_%s_file" % metric])  # byte-identical to the reference's file
+
+
+@pytest.mark.parametrize("quant", ["f32", "f16", "i8"])
+def test_lattice_files_byte_identical(eng, quant):
+    scale = 0.25 if quant == "i8" else 1.0
+    g = gpu_index(eng, LATTICE * scale, "l2sq", quant, M=12, efc=64, ef=32)
+    k, d, _ = g.search_batch(LATTICE * scale, 5)
+    same_up_to_ties(k, d, G["lattice_%s_keys" % quant], G["lattice_%s_dists" % quant])
+    assert np.array_equal(g.save_buffer(), G["lattice_%s_file" % quant])
+
+
+def test_lattice_bits(eng):
+    g = gpu_index(eng, int_bits(LATTICE), "hamming", "b1", M=12, efc=64, ef=32)
+    k, d, _ = g.search_batch(int_bits(LATTICE), 5)
+    assert np.array_equal(d, G["lattice_hamming_dists"])
+    sign_x = np.cos(np.arange(14 * 16).reshape(14, 16) * 0.7).astype(np.float32)
+    g = gpu_index(eng, sign_x, "l2sq", "b1", M=12, efc=64, ef=32)  # f32 in, sign bits stored, hamming distances out
+    k, d, _ = g.search_batch(sign_x, 5)
+    assert np.array_equal(d, G["lattice_signbits_dists"])
+
+
+@pytest.mark.parametrize("name,metric,M,efc,ef", [("rand_l2", "l2sq", 8, 48, 24), ("rand_cos", "cos", 6, 40, 20)])
+def test_reference_file_loads_and_sequential_build_reproduces_it(eng, name, metric, M, efc, ef):
+    X, Q = G[name + "_X"], G[name + "_Q"]
+    g = eng.Index(X.shape[1], metric, "f32", M=M, efc=efc, ef=ef)
+    g.load_buffer(G[name + "_file"])  # an index file written by the reference
+    k, d, _ = g.search_batch(Q, 10)
+    assert np.array_equal(k, G[name + "_keys"])
+    assert np.allclose(d, G[name + "_dists"], rtol=1e-6, atol=1e-6)
+    g2 = gpu_index(eng, X, metric, keys=1000 + np.arange(len(X)), M=M, efc=efc, ef=ef)
+    assert np.mean(g2.save_buffer() == G[name + "_file"]) > 0.999  # GPU build in reference order: same file
+    ek, ed = eng.exact_search(X, Q, 10, metric)
+    assert np.allclose(ed, G[name + "_exact_dists"], rtol=1e-6, atol=1e-6)
+
+
+def test_distance_kernels(eng, port):
+    A, B = G["dist_A"], G["dist_B"]
+    for metric in ("l2sq", "cos"):
+        mine = eng.distance_batch(A, B, metric)
+        assert np.allclose(mine, G["dist_f32_" + metric], rtol=1e-5, atol=1e-6)
+    assert mine[0] == 0.0 and mine[1] == 1.0
+    ba, bb = np.packbits(A > 0, axis=1), np.packbits(B > 0, axis=1)
+    assert np.array_equal(eng.distance_batch(ba, bb, "hamming", "b1", 40), G["dist_b1_hamming"])
+    assert eng.distance(np.array([0, 1, 1], np.float32), np.array([1, 1, 1], np.float32), "cos") == pytest.approx(0.183503, abs=1e-6)
+    for quant in ("f16", "i8", "b1"):
+        ca, cb = eng.cast(A[:24], quant), eng.cast(B[:24], quant)
+        assert np.array_equal(ca.view(np.uint8), port.cast_f32(A[:24], quant).view(np.uint8))  # bit-exact codecs
+        for metric in ("l2sq", "cos"):
+            mine = eng.distance_batch(ca, cb, metric, quant, 40)
+            assert np.allclose(mine, G["dist_%s_%s" % (quant, metric)], rtol=1e-5, atol=1e-5), (quant, metric)
+
+
+def test_casts_bit_exact_edge_values(eng, port):
+    v = np.array([[0.0, -0.0, 1e-8, -1e-8, 0.999, 1.0, 1.004, 1.006, -1.0, -1.009, 65504, 65520, 1e-5, 5.96e-8, 2.98e-8, 0.1,
+                   0.00999, 0.01, -0.0149, 3.14159, np.inf, -np.inf, 1e9, -1e9]], np.float32)
+    for quant in ("f16", "i8", "b1"):
+        assert np.array_equal(eng.cast(v, quant).view(np.uint8), port.cast_f32(v, quant).view(np.uint8)), quant
+    rng = np.random.default_rng(0)
+    r = (rng.standard_normal((200, 96)) * np.exp(rng.uniform(-12, 6, (200, 96)))).astype(np.float32)
+    for quant in ("f16", "i8", "b1"):
+        assert np.array_equal(eng.cast(r, quant).view(np.uint8), port.cast_f32(r, quant).view(np.uint8)), quant
+
+
+def test_pq_codec(eng, port):
+    X = (LATTICE * 0.1).astype(np.float32)
+    codes = eng.quantize_pq(PQ_CODEBOOK, X, 3)
+    assert np.array_equal(codes, port.pq_compress(PQ_CODEBOOK, X, 3))
+    assert np.array_equal(eng.dequantize_pq(PQ_CODEBOOK, codes), port.pq_decompress(PQ_CODEBOOK, codes))
+    rng = np.random.default_rng(4)
+    cb = rng.standard_normal((256, 64)).astype(np.float32)
+    V = rng.standard_normal((500, 64)).astype(np.float32)
+    for compat in (True, False):
+        mine = eng.quantize_pq(cb, V, 8, compat128=compat)
+        ref = port.pq_compress(cb, V, 8, compat128=compat)
+        assert np.mean(mine == ref) > 0.999  # argmin ties/rounding only
+        assert (mine.max() < 128) == compat
+    assert np.array_equal(eng.dequantize_pq(cb, ref), port.pq_decompress(cb, ref))
+
+
+def test_exact_search_matches_oracle(eng, port):
+    rng = np.random.default_rng(9)
+    X = rng.standard_normal((5000, 33)).astype(np.float32)  # odd dimension: padded rows
+    Q = rng.standard_normal((37, 33)).astype(np.float32)
+    for metric in ("l2sq", "cos"):
+        gk, gd = eng.exact_search(X, Q, 20, metric)
+        pk, pd = port.exact_search(X, Q, 20, metric)
+        assert np.array_equal(gk, pk)
+        assert np.allclose(gd, pd, rtol=1e-5, atol=1e-6)
+    b = rng.integers(0, 256, (3000, 24), dtype=np.uint8)
+    gk, gd = eng.exact_search(b, b[:10], 7, "hamming", "b1")
+    pk, pd = port.exact_search(b, b[:10], 7, "hamming", "b1")
+    assert np.array_equal(gk, pk) and np.array_equal(gd, pd)  # ties broken by lower offset on both sides
+
+
+def test_merge_kernel_matches_host_statement(eng):
+    import torch
+    from lantern_b200 import shard
+    rng = np.random.default_rng(1)
+    G_, nq, k = 8, 50, 10
+    d = np.sort(rng.random((G_, nq, k)).astype(np.float32), axis=2)
+    keys = rng.permutation(G_ * nq * k).reshape(G_, nq, k).astype(np.uint64)
+    keys[3, :, 7:] = shard.EMPTY_KEY  # a shard that found fewer than k
+    d[3, :, 7:] = np.inf
+    tk = torch.from_numpy(keys.astype(np.int64)).cuda()
+    td = torch.from_numpy(d).cuda()
+    ok = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    od = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    eng.merge_shards_device(tk.data_ptr(), td.data_ptr(), G_, nq, k, ok.data_ptr(), od.data_ptr())
+    torch.cuda.synchronize()
+    mk, md = shard.merge_topk_host(keys, d)
+    assert np.array_equal(ok.cpu().numpy().astype(np.uint64), mk) and np.array_equal(od.cpu().numpy(), md)
+
+
+def test_error_convention(eng):
+    with pytest.raises(eng.EngineError, match="hamming metric requires b1"):
+        eng.Index(8, "hamming", "f32")
+    with pytest.raises(eng.EngineError, match="connectivity"):
+        eng.Index(8, "l2sq", M=1)
+    g = eng.Index(8, "l2sq")
+    with pytest.raises(eng.EngineError, match="Reserve capacity"):
+        g.add(1, np.zeros(8, np.float32))  # index.hpp:2514-2517
+    k, d = g.search(np.zeros(8, np.float32), 3)  # empty index -> 0 results (index.hpp:2693)
+    assert len(k) == 0
+    with pytest.raises(eng.EngineError, match="bad magic"):
+        g.load_buffer(np.zeros(200, np.uint8))

@@ -1,0 +1,91 @@
+"""The plain-C restatement against the compiled reference itself (skipped where oracle/_ref is absent)."""
+import struct
+
+import numpy as np
+import pytest
+
+
+def trim(buf):
+    n, M, M0 = struct.unpack_from("<QQQ", buf, 80)
+    vsz, = struct.unpack_from("<Q", buf, 120)
+    off, b = 136, bytes(buf)
+    for _ in range(n):
+        lvl, = struct.unpack_from("<h", b, off + 8)
+        off += 10 + 4 + 6 * M0 + lvl * (4 + 6 * M) + vsz
+    return np.array(buf[:off])
+
+
+@pytest.mark.parametrize("n,d,M,efc,ef,metric", [(1500, 32, 16, 128, 64, "l2sq"), (2000, 24, 6, 40, 20, "l2sq"), (1200, 48, 16, 96, 50, "cos")])
+def test_build_and_search_byte_exact_on_integer_data(port, ref, n, d, M, efc, ef, metric):
+    rng = np.random.default_rng(n)
+    X = rng.integers(-8, 9, (n, d)).astype(np.float32)
+    Q = rng.integers(-8, 9, (150, d)).astype(np.float32)
+    r = ref.RefIndex(d, metric, M=M, efc=efc, ef=ef)
+    p = port.PortIndex(d, metric, M=M, efc=efc, ef=ef)
+    r.reserve(n), p.reserve(n)
+    for i in range(n):
+        r.add(i + 1, X[i]), p.add(i + 1, X[i])
+    assert np.array_equal(trim(r.save_buffer()), p.save_buffer())
+    for q in Q:
+        rk, rd = r.search(q, 10)
+        pk, pd, st = p.search(q, 10)
+        assert np.array_equal(rk, pk) and np.array_equal(rd, pd)
+
+
+def test_counters_match_reference(port, ref):
+    """computed_distances / visited_members (index.hpp:2726-2727) -- the quantity the roofline's algorithmic bytes use."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    X = rng.integers(-8, 9, (2000, 32)).astype(np.float32)
+    r = ref.RefIndex(32, "l2sq", M=16, efc=128, ef=64)
+    p = port.PortIndex(32, "l2sq", M=16, efc=128, ef=64)
+    r.reserve(2000), p.reserve(2000)
+    for i in range(2000):
+        r.add(i + 1, X[i]), p.add(i + 1, X[i])
+    L = ref.lib()
+    for q in rng.integers(-8, 9, (50, 32)).astype(np.float32):
+        keys, dists = np.zeros(10, np.uint64), np.zeros(10, np.float32)
+        comp, vis = C.c_uint64(), C.c_uint64()
+        L.refx_search_stats(r.h, q.ctypes.data, 10, keys.ctypes.data, dists.ctypes.data, C.byref(comp), C.byref(vis))
+        pk, pd, st = p.search(q, 10)
+        assert st.computed_distances == comp.value and st.visited_members == vis.value
+
+
+def test_float_data_ids_and_tolerance(port, ref):
+    rng = np.random.default_rng(11)
+    X = rng.standard_normal((1500, 64)).astype(np.float32)
+    r = ref.RefIndex(64, "cos", M=16, efc=128, ef=64)
+    r.reserve(1500)
+    for i in range(1500):
+        r.add(i + 1, X[i])
+    p = port.PortIndex(64, "cos", M=16, efc=128, ef=64)
+    p.reserve(1500)
+    p.load_buffer(trim(r.save_buffer()))  # same graph, the reference's own bytes
+    same = 0
+    for q in rng.standard_normal((200, 64)).astype(np.float32):
+        rk, rd = r.search(q, 10)
+        pk, pd, _ = p.search(q, 10)
+        assert np.allclose(rd, pd, rtol=1e-5, atol=1e-6)
+        same += np.array_equal(rk, pk)
+    assert same >= 198
+
+
+def test_pq_128_centroid_quirk(port, ref):
+    """codebook_t::compress never picks centroids >= 128 (signed char loop, lantern_storage.hpp:123)."""
+    rng = np.random.default_rng(2)
+    d, nsub, ncent = 16, 4, 256
+    cb = rng.standard_normal((ncent, d)).astype(np.float32)
+    X = rng.standard_normal((300, d)).astype(np.float32)
+    r = ref.RefIndex(d, "l2sq", M=8, efc=32, ef=300, pq=True, num_centroids=ncent, num_subvectors=nsub, codebook=cb)
+    r.reserve(300)
+    for i in range(300):
+        r.add(i + 1, X[i])
+    codes = port.pq_compress(cb, X, nsub, compat128=True)
+    assert codes.max() < 128
+    dec = port.pq_decompress(cb, codes)
+    q = rng.standard_normal(d).astype(np.float32)
+    rk, rd = r.search(q, 300)  # ef = N -> (almost) every node, distances = raw query vs decoded candidate
+    mine = ((dec[rk.astype(int) - 1] - q) ** 2).sum(1)
+    assert np.allclose(mine, rd, rtol=1e-5, atol=1e-6)
+    full = port.pq_compress(cb, X, nsub, compat128=False)
+    assert (full >= 128).any()
