@@ -43,6 +43,11 @@ WORKLOADS = {
                   desc="cfg2s (smoke-size): 100k x d768 f32 l2sq, M=16 efc=128 ef=64, batch-1024 k=10"),
     "cfg3": dict(n=10_000_000, dim=768, metric="cos", M=32, efc=128, ef=128, batch=4096, k=10,
                  desc="cfg3: 10M x d768 f32 cosine, M=32 efc=128 ef=128, batch-4096 k=10"),
+    # BASELINE configs[4] is 50M x 768-byte binary vectors over 8 GPUs: one shard's worth (6.25M) on one GPU
+    "cfg5s": dict(n=6_250_000, dim=6144, kind="b1", metric="hamming", M=16, efc=128, ef=64, batch=4096, k=10,
+                  desc="cfg5s (one of 8 shards of cfg5): 6.25M x 6144-bit (768 B) hamming, M=16 efc=128 ef=64, batch-4096 k=10"),
+    "cfg5t": dict(n=500_000, dim=6144, kind="b1", metric="hamming", M=16, efc=128, ef=64, batch=4096, k=10,
+                  desc="cfg5t (small): 500k x 6144-bit (768 B) hamming, M=16 efc=128 ef=64, batch-4096 k=10"),
 }
 METRIC_NAME = "queries/sec @ recall@10, d=768 fp32, 10M vectors, batch 4096, 1/2/4/8 B200"
 LATENT, NOISE = 32, 0.05
@@ -78,6 +83,34 @@ def structured_torch(n, dim, seed, device, chunk=200_000):
         z = torch.randn((hi - lo, LATENT), generator=g, device=device)
         out[lo:hi] = z @ P
         out[lo:hi] += NOISE * torch.randn((hi - lo, dim), generator=g, device=device)
+    return out
+
+
+def bits_torch(n, bits, seed, device, chunk=100_000, protos=64, flip=0.10):
+    """Binary vectors (SURVEY.md 8d cfg 5): one of 64 random prototypes XOR 10 % random bit flips, packed MSB-first."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(SEED_P)
+    proto = torch.randint(0, 256, (protos, bits // 8), generator=g, device=device, dtype=torch.uint8)
+    g.manual_seed(seed)
+    out = torch.empty((n, bits // 8), dtype=torch.uint8, device=device)
+    w = torch.tensor([128, 64, 32, 16, 8, 4, 2, 1], device=device, dtype=torch.uint8)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        which = torch.randint(0, protos, (hi - lo,), generator=g, device=device)
+        flips = (torch.rand((hi - lo, bits // 8, 8), generator=g, device=device) < flip).to(torch.uint8)
+        out[lo:hi] = proto[which] ^ (flips * w).sum(dim=2).to(torch.uint8)
+    return out
+
+
+def bits_np(n, bits, seed, chunk=100_000, protos=64, flip=0.10):
+    proto = np.random.default_rng(SEED_P).integers(0, 256, (protos, bits // 8), dtype=np.uint8)
+    rng = np.random.default_rng(seed)
+    out = np.empty((n, bits // 8), np.uint8)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        which = rng.integers(0, protos, hi - lo)
+        out[lo:hi] = proto[which] ^ np.packbits(rng.random((hi - lo, bits)) < flip, axis=1)
     return out
 
 
@@ -154,11 +187,12 @@ def run_reference(args, wl):
     # bounded sample: a prefix of the corpus the reference can index in about `--ref-build-seconds` with all cores;
     # the rate is measured on a pilot of 20k rows (it only falls slowly, ~log N, afterwards)
     pilot = min(wl["n"], 20_000)
-    X = structured_np(wl["n"] if args.ref_rows == 0 else min(wl["n"], args.ref_rows), wl["dim"], SEED_CORPUS)
+    gen = bits_np if wl.get("kind") == "b1" else structured_np
+    X = gen(wl["n"] if args.ref_rows == 0 else min(wl["n"], args.ref_rows), wl["dim"], SEED_CORPUS)
     nsteps = args.steps + args.warmup
     pool = min(nsteps, args.query_pool)
-    Q = structured_np(pool * wl["batch"], wl["dim"], SEED_QUERY)
-    idx = reflib.RefIndex(wl["dim"], wl["metric"], M=wl["M"], efc=wl["efc"], ef=wl["ef"], threads=cores)
+    Q = gen(pool * wl["batch"], wl["dim"], SEED_QUERY)
+    idx = reflib.RefIndex(wl["dim"], wl["metric"], wl.get("kind", "f32"), M=wl["M"], efc=wl["efc"], ef=wl["ef"], threads=cores)
     idx.reserve(len(X))
     keys = np.arange(1, len(X) + 1, dtype=np.uint64)
     t0 = time.perf_counter()
@@ -190,7 +224,7 @@ def run_reference(args, wl):
     line = {
         "impl": "reference", "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u8 (popcount)" if wl.get("kind") == "b1" else "f32", "data": "synthetic",
         "config": {"workload": wl["desc"], "corpus_rows_indexed": n_ref, "ef": wl["ef"], "k": wl["k"], "batch": wl["batch"],
                    "queries_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "reference", "sample": sample},
@@ -217,6 +251,9 @@ def run_ours(args, wl):
     api.lib()
 
     n, dim, k, ef, B = wl["n"], wl["dim"], wl["k"], wl["ef"], wl["batch"]
+    kind = wl.get("kind", "f32")
+    rowb = dim // 8 if kind == "b1" else dim * 4  # bytes of one input row
+    gen_t = bits_torch if kind == "b1" else structured_torch
     nsteps = args.steps + args.warmup
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
     pool = min(nsteps, args.query_pool)  # distinct query batches, cycled: step s uses batch s % pool
@@ -224,17 +261,17 @@ def run_ours(args, wl):
     # ---- corpus shard of this rank: contiguous row range ----
     lo, hi = (n * rank) // world, (n * (rank + 1)) // world
     t0 = time.perf_counter()
-    X = structured_torch(n, dim, SEED_CORPUS, dev)[lo:hi].contiguous() if world > 1 else structured_torch(n, dim, SEED_CORPUS, dev)
-    Q = structured_torch(pool * B, dim, SEED_QUERY, dev)
+    X = gen_t(n, dim, SEED_CORPUS, dev)[lo:hi].contiguous() if world > 1 else gen_t(n, dim, SEED_CORPUS, dev)
+    Q = gen_t(pool * B, dim, SEED_QUERY, dev)
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t0
 
     ef_shard = args.shard_ef if (world > 1 and args.shard_ef > 0) else ef
-    idx = api.Index(dim, wl["metric"], "f32", M=wl["M"], efc=wl["efc"], ef=ef)
+    idx = api.Index(dim, wl["metric"], kind, M=wl["M"], efc=wl["efc"], ef=ef)
     idx.reserve(hi - lo)
     keys_host = np.arange(lo + 1, hi + 1, dtype=np.uint64)  # global keys = row + 1
     t0 = time.perf_counter()
-    idx.add_batch_device(keys_host, X.data_ptr(), hi - lo, dim * 4, "f32")
+    idx.add_batch_device(keys_host, X.data_ptr(), hi - lo, rowb, kind)
     idx.build()
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t0
@@ -253,7 +290,7 @@ def run_ours(args, wl):
 
     def step_device(s):
         q = Q[(s % pool) * B:((s % pool) + 1) * B]
-        idx.search_batch_device(q.data_ptr(), B, dim * 4, "f32", k, state["ef"], out_keys.data_ptr(), out_dists.data_ptr(),
+        idx.search_batch_device(q.data_ptr(), B, rowb, kind, k, state["ef"], out_keys.data_ptr(), out_dists.data_ptr(),
                                 out_counts.data_ptr(), stream.cuda_stream)
         if world > 1:  # the one exchange step: all-gather of per-shard top-k over NVLink, then a G-way merge
             dist.all_gather_into_tensor(g_keys, out_keys)
@@ -272,8 +309,8 @@ def run_ours(args, wl):
     nrec = min(B, 1024)
     tk = torch.empty((nrec, k), dtype=torch.int64, device=dev)
     td = torch.empty((nrec, k), dtype=torch.float32, device=dev)
-    api.exact_search_device(X.data_ptr(), hi - lo, dim * 4, Q.data_ptr(), nrec, dim * 4, k, tk.data_ptr(), td.data_ptr(),
-                            wl["metric"], "f32", dim, stream.cuda_stream)
+    api.exact_search_device(X.data_ptr(), hi - lo, rowb, Q.data_ptr(), nrec, rowb, k, tk.data_ptr(), td.data_ptr(),
+                            wl["metric"], kind, dim, stream.cuda_stream)
     tk += lo + 1  # offsets -> global keys
     if world > 1:
         gk = torch.empty((world, nrec, k), dtype=torch.int64, device=dev)
@@ -295,15 +332,15 @@ def run_ours(args, wl):
         # every rank also builds the FULL graph (it fits in HBM): rank 0 takes the unsharded recall target from it, and all
         # ranks use it for the clearly-labelled "replicated" comparison below
         target = torch.zeros(1, dtype=torch.float64, device=dev)
-        Xfull = structured_torch(n, dim, SEED_CORPUS, dev)
-        full = api.Index(dim, wl["metric"], "f32", M=wl["M"], efc=wl["efc"], ef=ef)
+        Xfull = gen_t(n, dim, SEED_CORPUS, dev)
+        full = api.Index(dim, wl["metric"], kind, M=wl["M"], efc=wl["efc"], ef=ef)
         full.reserve(n)
-        full.add_batch_device(np.arange(1, n + 1, dtype=np.uint64), Xfull.data_ptr(), n, dim * 4, "f32")
+        full.add_batch_device(np.arange(1, n + 1, dtype=np.uint64), Xfull.data_ptr(), n, rowb, kind)
         full.build()
         del Xfull
         fk = torch.empty((B, k), dtype=torch.int64, device=dev)
         fd = torch.empty((B, k), dtype=torch.float32, device=dev)
-        full.search_batch_device(Q.data_ptr(), B, dim * 4, "f32", k, ef, fk.data_ptr(), fd.data_ptr(), 0, stream.cuda_stream)
+        full.search_batch_device(Q.data_ptr(), B, rowb, kind, k, ef, fk.data_ptr(), fd.data_ptr(), 0, stream.cuda_stream)
         torch.cuda.synchronize()
         if rank == 0:
             target[0] = recall_at_k(fk[:nrec].cpu().numpy(), truth)
@@ -332,13 +369,13 @@ def run_ours(args, wl):
         # no exchange step; weak scaling in queries.  Same kernel, same ef as 1 GPU, same recall as 1 GPU.
         reps = max(10, min(args.steps, 100))
         for s in range(3):
-            full.search_batch_device(Q[((s + rank) % pool) * B].data_ptr(), B, dim * 4, "f32", k, ef, fk.data_ptr(), fd.data_ptr(), 0,
+            full.search_batch_device(Q[((s + rank) % pool) * B].data_ptr(), B, rowb, kind, k, ef, fk.data_ptr(), fd.data_ptr(), 0,
                                      stream.cuda_stream)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for s in range(reps):
-            full.search_batch_device(Q[((s + rank) % pool) * B].data_ptr(), B, dim * 4, "f32", k, ef, fk.data_ptr(), fd.data_ptr(), 0,
+            full.search_batch_device(Q[((s + rank) % pool) * B].data_ptr(), B, rowb, kind, k, ef, fk.data_ptr(), fd.data_ptr(), 0,
                                      stream.cuda_stream)
         e1.record(stream)
         barrier()
@@ -385,7 +422,7 @@ def run_ours(args, wl):
     alg_bytes, kern_ms, n_dist, pops = 0, 0.0, 0, 0
     for s in range(args.warmup, nsteps):
         q = Q[(s % pool) * B:((s % pool) + 1) * B]
-        idx.search_batch_device(q.data_ptr(), B, dim * 4, "f32", k, ef_shard, out_keys.data_ptr(), out_dists.data_ptr(),
+        idx.search_batch_device(q.data_ptr(), B, rowb, kind, k, ef_shard, out_keys.data_ptr(), out_dists.data_ptr(),
                                 out_counts.data_ptr(), stream.cuda_stream)
         st = idx.last_stats()
         alg_bytes += st["algorithmic_bytes"]; kern_ms += st["kernel_ms"]; n_dist += st["computed_distances"]; pops += st["base_pops"]
@@ -400,22 +437,22 @@ def run_ours(args, wl):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": "hnsw_search_kernel<l2sq|cos,f32,NQ=6>",
+                "peak_source": peak_src, "kernel": "hnsw_search_kernel<%s,%s>" % (wl["metric"], kind),
                 "kernel_ms_per_step": kern_ms / args.steps, "algorithmic_bytes_per_step": alg_bytes / args.steps,
                 "dist_evals_per_query": n_dist / (args.steps * B), "pops_per_query": pops / (args.steps * B)}
 
     # ---- e2e through the reference-facing host call: pinned host buffers in/out, copies inside the timed region ----
     e2e = None
     if world > 1:
-        hq = torch.empty((pool * B, dim), dtype=torch.float32).pin_memory()
+        hq = torch.empty(Q.shape, dtype=Q.dtype).pin_memory()
         hq.copy_(Q)
-        dq = torch.empty((B, dim), dtype=torch.float32, device=dev)
+        dq = torch.empty((B, Q.shape[1]), dtype=Q.dtype, device=dev)
         hk = torch.empty((B, k), dtype=torch.int64).pin_memory()
         hd = torch.empty((B, k), dtype=torch.float32).pin_memory()
 
         def step_e2e(s):
             dq.copy_(hq[(s % pool) * B:((s % pool) + 1) * B], non_blocking=True)  # every shard needs every query
-            idx.search_batch_device(dq.data_ptr(), B, dim * 4, "f32", k, ef_shard, out_keys.data_ptr(), out_dists.data_ptr(),
+            idx.search_batch_device(dq.data_ptr(), B, rowb, kind, k, ef_shard, out_keys.data_ptr(), out_dists.data_ptr(),
                                     out_counts.data_ptr(), stream.cuda_stream)
             dist.all_gather_into_tensor(g_keys, out_keys)
             dist.all_gather_into_tensor(g_dists, out_dists)
@@ -436,35 +473,35 @@ def run_ours(args, wl):
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dt = float(dt.item())
-        e2e = {"value": args.steps * B / dt, "unit": "queries/s", "h2d_bytes_per_step": world * B * dim * 4,
+        e2e = {"value": args.steps * B / dt, "unit": "queries/s", "h2d_bytes_per_step": world * B * rowb,
                "d2h_bytes_per_step": B * k * 12, "ms_per_step": 1e3 * dt / args.steps,
                "note": "every rank uploads the query batch from pinned host memory; rank 0 downloads the merged top-k"}
     if world == 1:
-        hq = torch.empty((pool * B, dim), dtype=torch.float32).pin_memory()
+        hq = torch.empty(Q.shape, dtype=Q.dtype).pin_memory()
         hq.copy_(Q)
         hk = torch.empty((B, k), dtype=torch.int64).pin_memory()
         hd = torch.empty((B, k), dtype=torch.float32).pin_memory()
         hc = torch.empty((B,), dtype=torch.int64).pin_memory()
         for s in range(args.warmup):
-            idx.search_batch_raw(hq[(s % pool) * B].data_ptr(), B, dim * 4, "f32", k, ef, hk.data_ptr(), hd.data_ptr(), hc.data_ptr())
+            idx.search_batch_raw(hq[(s % pool) * B].data_ptr(), B, rowb, kind, k, ef, hk.data_ptr(), hd.data_ptr(), hc.data_ptr())
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for s in range(args.warmup, nsteps):
-            idx.search_batch_raw(hq[(s % pool) * B].data_ptr(), B, dim * 4, "f32", k, ef, hk.data_ptr(), hd.data_ptr(), hc.data_ptr())
+            idx.search_batch_raw(hq[(s % pool) * B].data_ptr(), B, rowb, kind, k, ef, hk.data_ptr(), hd.data_ptr(), hc.data_ptr())
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        e2e = {"value": args.steps * B / dt, "unit": "queries/s", "h2d_bytes_per_step": B * dim * 4,
+        e2e = {"value": args.steps * B / dt, "unit": "queries/s", "h2d_bytes_per_step": B * rowb,
                "d2h_bytes_per_step": B * k * 8 + B * k * 4 + B * 4, "ms_per_step": 1e3 * dt / args.steps}
 
     # ---- CPU baseline (rank 0, N=1): the unmodified reference on the host cores over the SAME index file ----
     cpu_baseline, parity = None, None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and n * rowb <= 8e9:  # the reference needs the index file twice in host RAM
         from oracle import reflib
         if reflib.available():
             cores = reflib.lib().refx_hardware_threads()
             t0 = time.perf_counter()
             buf = idx.save_buffer()
-            ridx = reflib.RefIndex(dim, wl["metric"], M=wl["M"], efc=wl["efc"], ef=ef, threads=cores)
+            ridx = reflib.RefIndex(dim, wl["metric"], kind, M=wl["M"], efc=wl["efc"], ef=ef, threads=cores)
             ridx.load_buffer(buf)
             t_load = time.perf_counter() - t0
             del buf
@@ -487,7 +524,7 @@ def run_ours(args, wl):
                                       "%d of the bench's query batches (%d queries, %.1f s) on %d threads" % (
                                           n, t_load, s, done, spent, cores)}
             # same-graph parity at full size: step-0 queries, ids position-wise
-            idx.search_batch_device(Q.data_ptr(), B, dim * 4, "f32", k, ef, out_keys.data_ptr(), out_dists.data_ptr(),
+            idx.search_batch_device(Q.data_ptr(), B, rowb, kind, k, ef, out_keys.data_ptr(), out_dists.data_ptr(),
                                     out_counts.data_ptr(), stream.cuda_stream)
             torch.cuda.synchronize()
             st0 = idx.last_stats()
@@ -504,11 +541,12 @@ def run_ours(args, wl):
         line = {
             "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u8 (popcount)" if kind == "b1" else "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "corpus_rows": n, "rows_per_gpu": hi - lo, "ef": ef, "ef_per_shard": ef_shard, "k": k,
                        "batch": B, "parallelism": "row-range shards x%d + NCCL all-gather of top-k + merge" % world if world > 1 else "1 GPU",
-                       "l2_policy": "inputs larger than L2: %.1f GB corpus gathered at random; %d distinct query batches cycled" % ((hi - lo) * dim * 4 / 1e9, pool),
-                       "generator": "x = z P + %.2f eps, z~N(0,I_%d), seeds %d/%d/%d" % (NOISE, LATENT, SEED_P, SEED_CORPUS, SEED_QUERY)},
+                       "l2_policy": "inputs larger than L2: %.1f GB corpus gathered at random; %d distinct query batches cycled" % ((hi - lo) * rowb / 1e9, pool),
+                       "generator": ("64 random prototypes XOR 10%% bit flips, seeds %d/%d/%d" % (SEED_P, SEED_CORPUS, SEED_QUERY)) if kind == "b1" else
+                       "x = z P + %.2f eps, z~N(0,I_%d), seeds %d/%d/%d" % (NOISE, LATENT, SEED_P, SEED_CORPUS, SEED_QUERY)},
             "recall_at_10": rec, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "parity": parity, "sharding": shard_info,
             "build": {"vectors_per_s": (hi - lo) / t_build, "seconds": t_build, "datagen_seconds": t_gen},

@@ -37,6 +37,8 @@ struct BuildLaunch {
     uint32_t* upper_adj;
     uint32_t u0, count;        // batch = nodes [u0, u0 + count)
     const int32_t* new_levels; // [count]
+    const uint8_t* values;     // value (query side) of batch item i at values + i * value_stride
+    size_t value_stride;
     uint32_t efc;
     uint32_t top_cap;
     uint32_t req_stride; // requests per batch item = M * (max_level + 1)
@@ -50,11 +52,11 @@ struct BuildLaunch {
     uint32_t total_reqs;
 };
 
-template <int DM, int SK, int NQ>
+template <class W>
 __global__ void __launch_bounds__(kWalkThreads) build_insert_kernel(const BuildLaunch p, const uint32_t R) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    const WalkLayout lay = walk_layout(R, p.g.row_bytes, p.top_cap, p.g.M0 + 1);
-    Walker<DM, SK, NQ> w;
+    const WalkLayout lay = W::layout(p.g, R, p.top_cap, p.g.M0 + 1);
+    W w;
     w.init(p.g, smem_raw, lay, R, p.s);
     WalkSmem& sm = w.sm;
     const uint32_t M = p.g.M, M0 = p.g.M0;
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(kWalkThreads) build_insert_kernel(const BuildL
             break;
         const uint32_t u = p.u0 + item;
         const int lu = p.new_levels[item];
-        const uint8_t* urow = p.g.vectors + (size_t)u * p.g.row_bytes;
+        const uint8_t* urow = p.values + (size_t)item * p.value_stride;
         w.load_value(urow);
 
         uint32_t cur = p.g.entry;
@@ -113,12 +115,12 @@ __global__ void segment_heads_kernel(const unsigned long long* __restrict__ keys
         seg_start[atomicAdd(nseg, 1u)] = i;
 }
 
-template <int DM, int SK, int NQ>
+template <class W>
 __global__ void __launch_bounds__(kWalkThreads) build_reverse_kernel(const BuildLaunch p, const uint32_t R) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t M = p.g.M, M0 = p.g.M0;
-    const WalkLayout lay = walk_layout(R, p.g.row_bytes, M0 + 2, M0 + 1);
-    Walker<DM, SK, NQ> w;
+    const WalkLayout lay = W::layout(p.g, R, M0 + 2, M0 + 1);
+    W w;
     w.init(p.g, smem_raw, lay, R, p.s);
     WalkSmem& sm = w.sm;
     uint32_t* lst_i = reinterpret_cast<uint32_t*>(smem_raw + lay.total);
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(kWalkThreads) build_reverse_kernel(const Build
                 continue;
             }
             if (!have_d) { // distances target -> each current neighbour (index.hpp:3196-3198)
-                w.load_value(p.g.vectors + (size_t)v * p.g.row_bytes);
+                w.load_node(v);
                 for (uint32_t j = threadIdx.x; j < cnt; j += kWalkThreads)
                     sm.cand_id[j] = lst_i[j];
                 __syncthreads();
@@ -229,8 +231,6 @@ void build_pending(Index& idx) {
     if (!P)
         return;
     const IndexConfig& cfg = idx.cfg_;
-    if (cfg.pq)
-        throw CudaError("GPU build of a pq index: not implemented yet");
     const size_t n0 = idx.n_;
     const uint32_t M = (uint32_t)cfg.M, M0 = (uint32_t)cfg.M0;
     cudaStream_t stream = 0;
@@ -260,16 +260,20 @@ void build_pending(Index& idx) {
     // ---- kernel geometry ----
     const uint32_t row_bytes = (uint32_t)idx.row_bytes_;
     const uint32_t R = pick_ring_slots(row_bytes);
-    const int nq = pick_nq(row_bytes);
+    const int nq = cfg.pq ? 1 : pick_nq(row_bytes);
     if (nq < 0)
         throw CudaError("build: vectors wider than 8192 bytes are not supported");
     const uint32_t top_cap = (uint32_t)std::max<size_t>(cfg.efc, M0 + 2);
-    const size_t smem_ins = walk_layout(R, row_bytes, top_cap, M0 + 1).total;
-    const size_t smem_rev = walk_layout(R, row_bytes, M0 + 2, M0 + 1).total + (size_t)M0 * 8;
+    const GraphView gv0 = idx.view();
+    const size_t smem_ins = cfg.pq ? walk_layout_pq(gv0.num_subvectors, gv0.num_centroids, gv0.dims, top_cap, M0 + 1).total
+                                   : walk_layout(R, row_bytes, top_cap, M0 + 1).total;
+    const size_t smem_rev = (cfg.pq ? walk_layout_pq(gv0.num_subvectors, gv0.num_centroids, gv0.dims, M0 + 2, M0 + 1).total
+                                    : walk_layout(R, row_bytes, M0 + 2, M0 + 1).total) + (size_t)M0 * 8;
     int occ_ins = 0, occ_rev = 0;
-    dispatch_walk(idx.dist_mode_, cfg.scalar_kind, nq, [&](auto dm, auto sk, auto n) {
-        auto k1 = build_insert_kernel<decltype(dm)::value, decltype(sk)::value, decltype(n)::value>;
-        auto k3 = build_reverse_kernel<decltype(dm)::value, decltype(sk)::value, decltype(n)::value>;
+    dispatch_walker(cfg.pq, idx.dist_mode_, cfg.scalar_kind, nq, [&](auto tag) {
+        using W = typename decltype(tag)::type;
+        auto k1 = build_insert_kernel<W>;
+        auto k3 = build_reverse_kernel<W>;
         LB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ins));
         LB_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rev));
         LB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ins, k1, kWalkThreads, smem_ins));
@@ -321,6 +325,13 @@ void build_pending(Index& idx) {
         p.adj0 = idx.d_adj0_, p.upper_adj = idx.d_upper_adj_;
         p.u0 = u0, p.count = (uint32_t)bsz;
         p.new_levels = d_levels.p + pos;
+        if (cfg.pq) { // value = the raw f32 vector; stored side = codes
+            p.value_stride = round_up(cfg.dims * 4, 16);
+            p.values = (const uint8_t*)idx.d_pending_raw_ + pos * p.value_stride;
+        } else {
+            p.value_stride = row_bytes;
+            p.values = idx.d_vectors_ + (size_t)u0 * row_bytes;
+        }
         p.efc = (uint32_t)cfg.efc, p.top_cap = top_cap;
         p.req_stride = req_stride;
         p.req_keys = req_keys.p, p.req_vals = req_vals.p;
@@ -329,9 +340,8 @@ void build_pending(Index& idx) {
         p.total_reqs = (uint32_t)nreq;
 
         const uint32_t grid_ins = (uint32_t)std::min<size_t>(bsz, (size_t)occ_ins * sms);
-        dispatch_walk(idx.dist_mode_, cfg.scalar_kind, nq, [&](auto dm, auto sk, auto n) {
-            build_insert_kernel<decltype(dm)::value, decltype(sk)::value, decltype(n)::value>
-                <<<grid_ins, kWalkThreads, smem_ins, stream>>>(p, R);
+        dispatch_walker(cfg.pq, idx.dist_mode_, cfg.scalar_kind, nq, [&](auto tag) {
+            build_insert_kernel<typename decltype(tag)::type><<<grid_ins, kWalkThreads, smem_ins, stream>>>(p, R);
         });
         LB_CUDA(cudaGetLastError());
         count_launch();
@@ -350,9 +360,8 @@ void build_pending(Index& idx) {
         count_launch();
         LB_CUDA(cudaMemsetAsync(idx.scratch_.counters, 0, sizeof(unsigned long long), stream));
         const uint32_t grid_rev = (uint32_t)std::min<size_t>(nreq, (size_t)occ_rev * sms);
-        dispatch_walk(idx.dist_mode_, cfg.scalar_kind, nq, [&](auto dm, auto sk, auto n) {
-            build_reverse_kernel<decltype(dm)::value, decltype(sk)::value, decltype(n)::value>
-                <<<grid_rev, kWalkThreads, smem_rev, stream>>>(p, R);
+        dispatch_walker(cfg.pq, idx.dist_mode_, cfg.scalar_kind, nq, [&](auto tag) {
+            build_reverse_kernel<typename decltype(tag)::type><<<grid_rev, kWalkThreads, smem_rev, stream>>>(p, R);
         });
         LB_CUDA(cudaGetLastError());
         count_launch();
@@ -366,6 +375,10 @@ void build_pending(Index& idx) {
     }
     idx.pending_n_ = 0;
     LB_CUDA(cudaStreamSynchronize(stream));
+    if (idx.d_pending_raw_) { // raw rows are only needed while inserting
+        LB_CUDA(cudaFree(idx.d_pending_raw_));
+        idx.d_pending_raw_ = nullptr, idx.pending_raw_cap_ = 0;
+    }
 }
 
 } // namespace lb200

@@ -111,7 +111,45 @@ __global__ void pq_decode_kernel(const float* __restrict__ codebook, uint32_t di
     }
 }
 
+// pair[s][a][b] = |c_a,s - c_b,s|^2 (l2sq) or c_a,s . c_b,s (cos); norm[s][c] = |c_c,s|^2
+__global__ void pq_tables_kernel(const float* __restrict__ codebook, uint32_t dims, uint32_t ncent, uint32_t nsub, int cosine,
+                                 float* __restrict__ pair, float* __restrict__ norm) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)nsub * ncent * ncent;
+    if (e >= total)
+        return;
+    const uint32_t b = (uint32_t)(e % ncent), a = (uint32_t)((e / ncent) % ncent), s = (uint32_t)(e / ((size_t)ncent * ncent));
+    const uint32_t sd = dims / nsub;
+    const float* ca = codebook + (size_t)a * dims + (size_t)s * sd;
+    const float* cb = codebook + (size_t)b * dims + (size_t)s * sd;
+    float acc = 0.f;
+    for (uint32_t i = 0; i < sd; ++i) {
+        if (cosine)
+            acc = fmaf(ca[i], cb[i], acc);
+        else {
+            const float d = ca[i] - cb[i];
+            acc = fmaf(d, d, acc);
+        }
+    }
+    pair[e] = acc;
+    if (a == b) {
+        float n2 = 0.f;
+        for (uint32_t i = 0; i < sd; ++i)
+            n2 = fmaf(ca[i], ca[i], n2);
+        norm[(size_t)s * ncent + a] = n2;
+    }
+}
+
 } // namespace
+
+void launch_pq_tables(const float* d_codebook, size_t dims, size_t ncent, size_t nsub, bool cosine, float* d_pair, float* d_norm,
+                      cudaStream_t stream) {
+    const size_t total = nsub * ncent * ncent;
+    pq_tables_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_codebook, (uint32_t)dims, (uint32_t)ncent, (uint32_t)nsub,
+                                                                        cosine ? 1 : 0, d_pair, d_norm);
+    LB_CUDA(cudaGetLastError());
+    count_launch();
+}
 
 void launch_cast_rows(const void* d_in, size_t in_stride, int in_kind, void* d_out, size_t out_stride, int out_kind,
                       size_t dims, size_t n, cudaStream_t stream) {

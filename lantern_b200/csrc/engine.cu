@@ -67,6 +67,11 @@ Index::Index(const IndexConfig& cfg, const float* codebook) : cfg_(cfg) {
         row_bytes_ = round_up(cfg.num_subvectors, 16);
         LB_CUDA(cudaMalloc(&d_codebook_, cfg.num_centroids * cfg.dims * sizeof(float)));
         LB_CUDA(cudaMemcpy(d_codebook_, codebook, cfg.num_centroids * cfg.dims * sizeof(float), cudaMemcpyHostToDevice));
+        LB_CUDA(cudaMalloc(&d_pq_pair_, cfg.num_subvectors * cfg.num_centroids * cfg.num_centroids * sizeof(float)));
+        LB_CUDA(cudaMalloc(&d_pq_norm_, cfg.num_subvectors * cfg.num_centroids * sizeof(float)));
+        launch_pq_tables(d_codebook_, cfg.dims, cfg.num_centroids, cfg.num_subvectors, dist_mode_ == DM_COS, d_pq_pair_, d_pq_norm_, 0);
+        if ((cfg.num_subvectors * cfg.num_centroids + cfg.dims) * 4 > 200 * 1024)
+            throw CudaError("pq: num_subvectors * num_centroids look-up table does not fit in shared memory");
     } else {
         stored_bytes_ = vec_bytes_;
         row_bytes_ = round_up(vec_bytes_, 16);
@@ -81,6 +86,7 @@ Index::~Index() {
     cudaFree(d_vectors_), cudaFree(d_adj0_), cudaFree(d_upper_ref_), cudaFree(d_upper_adj_), cudaFree(d_keys_);
     cudaFree(d_codebook_), cudaFree(scratch_.visited), cudaFree(scratch_.touched), cudaFree(scratch_.counters);
     cudaFree(d_query_buf_), cudaFree(d_io_buf_);
+    cudaFree(d_pq_pair_), cudaFree(d_pq_norm_), cudaFree(d_pending_raw_);
     if (h_pinned_)
         cudaFreeHost(h_pinned_);
     if (ev0_)
@@ -173,9 +179,24 @@ void Index::add_device(const uint64_t* host_keys, const void* d_vectors, size_t 
     if (cfg_.pq) {
         if (kind != SK_F32)
             throw CudaError("pq index takes f32 vectors");
+        if (stride % sizeof(float))
+            throw CudaError("pq index: vector stride must be a multiple of 4 bytes");
+        // stored side: codes (codebook_t::compress, with the reference's 128-centroid loop quirk, lantern_storage.hpp:123)
         launch_pq_encode(d_codebook_, cfg_.dims, cfg_.num_centroids, cfg_.num_subvectors, (const float*)d_vectors,
                          stride / sizeof(float), n, d_vectors_ + used * row_bytes_, row_bytes_, /*compat128=*/true, 0);
-        // zero padding of the code rows was done by ensure_capacity's memset
+        // value side of the build distances: the raw f32 vector (index_dense.hpp:1423-1425), kept until lb200_build
+        const size_t raw_row = round_up(cfg_.dims * 4, 16);
+        if ((pending_n_ + n) * raw_row > pending_raw_cap_) {
+            size_t nc = std::max((pending_n_ + n) * raw_row, pending_raw_cap_ * 2);
+            float* np = nullptr;
+            LB_CUDA(cudaMalloc(&np, nc));
+            if (d_pending_raw_ && pending_n_)
+                LB_CUDA(cudaMemcpy(np, d_pending_raw_, pending_n_ * raw_row, cudaMemcpyDeviceToDevice));
+            if (d_pending_raw_)
+                LB_CUDA(cudaFree(d_pending_raw_));
+            d_pending_raw_ = np, pending_raw_cap_ = nc;
+        }
+        launch_cast_rows(d_vectors, stride, SK_F32, (uint8_t*)d_pending_raw_ + pending_n_ * raw_row, raw_row, SK_F32, cfg_.dims, n, 0);
     } else {
         launch_cast_rows(d_vectors, stride, kind, d_vectors_ + used * row_bytes_, row_bytes_, cfg_.scalar_kind, cfg_.dims, n, 0);
     }
@@ -217,6 +238,8 @@ GraphView Index::view() const {
     g.entry = entry_;
     g.max_level = max_level_;
     g.codebook = d_codebook_;
+    g.pq_pair = d_pq_pair_;
+    g.pq_norm = d_pq_norm_;
     g.dims = (uint32_t)cfg_.dims;
     g.num_centroids = (uint32_t)cfg_.num_centroids;
     g.num_subvectors = (uint32_t)cfg_.num_subvectors;
@@ -264,14 +287,12 @@ void Index::search_device(const void* d_queries, size_t nq, size_t stride, int k
         L = k; // index.hpp:2706
     if (L > 4096)
         throw CudaError("search: max(ef, count) > 4096 is not supported");
-    if (cfg_.pq)
-        throw CudaError("search over a pq index: not implemented yet");
+    // queries -> storage scalar kind, 16-byte padded rows (index_dense.hpp:1435-1441); pq: the raw f32 query is the value
+    const size_t qrow = cfg_.pq ? round_up(cfg_.dims * 4, 16) : row_bytes_;
+    uint8_t* qbuf = query_buffer(nq * qrow);
+    launch_cast_rows(d_queries, stride, kind, qbuf, qrow, cfg_.pq ? (int)SK_F32 : cfg_.scalar_kind, cfg_.dims, nq, stream);
 
-    // queries -> storage scalar kind, 16-byte padded rows (index_dense.hpp:1435-1441)
-    uint8_t* qbuf = query_buffer(nq * row_bytes_);
-    launch_cast_rows(d_queries, stride, kind, qbuf, row_bytes_, cfg_.scalar_kind, cfg_.dims, nq, stream);
-
-    const uint32_t max_ctas = search_max_ctas(dist_mode_, cfg_.scalar_kind, (uint32_t)row_bytes_, (uint32_t)L, (uint32_t)cfg_.M0, false);
+    const uint32_t max_ctas = search_max_ctas(dist_mode_, cfg_.scalar_kind, view(), (uint32_t)L, cfg_.pq);
     ensure_scratch(max_ctas);
     LB_CUDA(cudaMemsetAsync(scratch_.counters, 0, 4 * sizeof(unsigned long long), stream));
 
@@ -280,11 +301,11 @@ void Index::search_device(const void* d_queries, size_t nq, size_t stride, int k
     p.s = scratch_;
     p.s.ctas = max_ctas;
     p.queries = qbuf;
-    p.query_stride = (uint32_t)row_bytes_;
+    p.query_stride = (uint32_t)qrow;
     p.nq = (uint32_t)nq, p.k = (uint32_t)k, p.L = (uint32_t)L;
     p.out_keys = d_keys, p.out_dists = d_dists, p.out_counts = d_counts;
     LB_CUDA(cudaEventRecord(ev0_, stream));
-    launch_search(dist_mode_, cfg_.scalar_kind, p, stream);
+    launch_search(dist_mode_, cfg_.scalar_kind, cfg_.pq, p, stream);
     LB_CUDA(cudaEventRecord(ev1_, stream));
     last_nq_ = (uint32_t)nq;
 }

@@ -52,6 +52,8 @@ struct GraphView {
     int32_t max_level;
     // PQ (row_bytes then is the padded code width)
     const float* codebook; // [num_centroids][dims]
+    const float* pq_pair;  // [nsub][ncent][ncent] centroid-pair table (l2sq: |ca-cb|^2 ; cos: ca.cb)
+    const float* pq_norm;  // [nsub][ncent] |centroid slice|^2 (cos)
     uint32_t flags;        // tuning: 1 = prefetch adjacency of every measured node, 2 = of accepted nodes only, 4 = evict-first rows
     uint32_t dims, num_centroids, num_subvectors;
 };
@@ -121,6 +123,10 @@ class Index {
     size_t upper_lists_ = 0, upper_lists_cap_ = 0; // number of M-wide lists in d_upper_adj_
     uint64_t* d_keys_ = nullptr;
     float* d_codebook_ = nullptr;
+    float* d_pq_pair_ = nullptr;
+    float* d_pq_norm_ = nullptr;
+    float* d_pending_raw_ = nullptr; // pq: raw f32 rows of the pending vectors (the value side of build distances)
+    size_t pending_raw_cap_ = 0;
     // host mirrors of the small per-node metadata
     std::vector<int16_t> h_levels_;
     std::vector<uint64_t> h_keys_;
@@ -155,6 +161,8 @@ void launch_cast_rows(const void* d_in, size_t in_stride, int in_kind, void* d_o
 void launch_pq_encode(const float* d_codebook, size_t dims, size_t ncent, size_t nsub, const float* d_vecs,
                       size_t vec_stride_floats, size_t n, uint8_t* d_codes, size_t code_stride, bool compat128,
                       cudaStream_t stream);
+void launch_pq_tables(const float* d_codebook, size_t dims, size_t ncent, size_t nsub, bool cosine, float* d_pair, float* d_norm,
+                      cudaStream_t stream);
 void launch_pq_decode(const float* d_codebook, size_t dims, size_t ncent, size_t nsub, const uint8_t* d_codes,
                       size_t code_stride, size_t n, float* d_vecs, cudaStream_t stream);
 // search.cu
@@ -168,8 +176,8 @@ struct SearchLaunch {
     float* out_dists;
     uint32_t* out_counts;
 };
-uint32_t search_max_ctas(int dist_mode, int scalar_kind, uint32_t row_bytes, uint32_t L, uint32_t M0, bool pq);
-void launch_search(int dist_mode, int scalar_kind, const SearchLaunch& p, cudaStream_t stream);
+uint32_t search_max_ctas(int dist_mode, int scalar_kind, const GraphView& g, uint32_t L, bool pq);
+void launch_search(int dist_mode, int scalar_kind, bool pq, const SearchLaunch& p, cudaStream_t stream);
 // exact.cu
 void launch_exact(int dist_mode, int scalar_kind, const uint8_t* d_data, size_t n, size_t data_stride,
                   const uint8_t* d_queries, size_t nq, size_t q_stride, uint32_t row_bytes, size_t k, uint64_t* d_keys,

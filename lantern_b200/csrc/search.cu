@@ -26,11 +26,11 @@ namespace lb200 {
 
 namespace {
 
-template <int DM, int SK, int NQ>
+template <class W>
 __global__ void __launch_bounds__(kWalkThreads) hnsw_search_kernel(const SearchLaunch p, const uint32_t R) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    const WalkLayout lay = walk_layout(R, p.g.row_bytes, p.L, p.g.M0);
-    Walker<DM, SK, NQ> w;
+    const WalkLayout lay = W::layout(p.g, R, p.L, p.g.M0);
+    W w;
     w.init(p.g, smem_raw, lay, R, p.s);
     WalkSmem& sm = w.sm;
 
@@ -73,16 +73,16 @@ __global__ void __launch_bounds__(kWalkThreads) hnsw_search_kernel(const SearchL
     }
 }
 
-template <int DM, int SK, int NQ> void launch_one(const SearchLaunch& p, uint32_t R, size_t smem, uint32_t grid, cudaStream_t stream) {
-    auto kern = hnsw_search_kernel<DM, SK, NQ>;
+template <class W> void launch_one(const SearchLaunch& p, uint32_t R, size_t smem, uint32_t grid, cudaStream_t stream) {
+    auto kern = hnsw_search_kernel<W>;
     LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kWalkThreads, smem, stream>>>(p, R);
     LB_CUDA(cudaGetLastError());
     count_launch();
 }
 
-template <int DM, int SK, int NQ> int occupancy_one(size_t smem) {
-    auto kern = hnsw_search_kernel<DM, SK, NQ>;
+template <class W> int occupancy_one(size_t smem) {
+    auto kern = hnsw_search_kernel<W>;
     LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = 0;
     LB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, kWalkThreads, smem));
@@ -91,30 +91,30 @@ template <int DM, int SK, int NQ> int occupancy_one(size_t smem) {
 
 } // namespace
 
-uint32_t search_max_ctas(int dist_mode, int scalar_kind, uint32_t row_bytes, uint32_t L, uint32_t M0, bool pq) {
-    (void)pq;
-    const uint32_t R = pick_ring_slots(row_bytes);
-    const int nq = pick_nq(row_bytes);
+static size_t search_smem(const GraphView& g, bool pq, uint32_t R, uint32_t L) {
+    return pq ? walk_layout_pq(g.num_subvectors, g.num_centroids, g.dims, L, g.M0).total : walk_layout(R, g.row_bytes, L, g.M0).total;
+}
+
+uint32_t search_max_ctas(int dist_mode, int scalar_kind, const GraphView& g, uint32_t L, bool pq) {
+    const uint32_t R = pick_ring_slots(g.row_bytes);
+    const int nq = pq ? 1 : pick_nq(g.row_bytes);
     if (nq < 0)
         throw CudaError("search: vectors wider than 8192 bytes are not supported");
-    const size_t smem = walk_layout(R, row_bytes, L, M0).total;
+    const size_t smem = search_smem(g, pq, R, L);
     int occ = 0;
-    dispatch_walk(dist_mode, scalar_kind, nq, [&](auto dm, auto sk, auto n) {
-        occ = occupancy_one<decltype(dm)::value, decltype(sk)::value, decltype(n)::value>(smem);
-    });
+    dispatch_walker(pq, dist_mode, scalar_kind, nq, [&](auto tag) { occ = occupancy_one<typename decltype(tag)::type>(smem); });
     if (occ < 1)
-        throw CudaError("search: kernel does not fit on an SM (ef/k too large for shared memory?)");
+        throw CudaError("search: kernel does not fit on an SM (ef/k or the pq table too large for shared memory)");
     return (uint32_t)occ * (uint32_t)device_sm_count();
 }
 
-void launch_search(int dist_mode, int scalar_kind, const SearchLaunch& p, cudaStream_t stream) {
+void launch_search(int dist_mode, int scalar_kind, bool pq, const SearchLaunch& p, cudaStream_t stream) {
     const uint32_t R = pick_ring_slots(p.g.row_bytes);
-    const int nq = pick_nq(p.g.row_bytes);
-    const size_t smem = walk_layout(R, p.g.row_bytes, p.L, p.g.M0).total;
+    const int nq = pq ? 1 : pick_nq(p.g.row_bytes);
+    const size_t smem = search_smem(p.g, pq, R, p.L);
     const uint32_t grid = p.s.ctas < p.nq ? p.s.ctas : p.nq;
-    dispatch_walk(dist_mode, scalar_kind, nq, [&](auto dm, auto sk, auto n) {
-        launch_one<decltype(dm)::value, decltype(sk)::value, decltype(n)::value>(p, R, smem, grid, stream);
-    });
+    dispatch_walker(pq, dist_mode, scalar_kind, nq,
+                    [&](auto tag) { launch_one<typename decltype(tag)::type>(p, R, smem, grid, stream); });
 }
 
 } // namespace lb200

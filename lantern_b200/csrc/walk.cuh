@@ -51,12 +51,12 @@ struct WalkLayout {
     size_t full, top_d, top_i, cand_id, cand_d, ctrl, total;
 };
 
-// R ring slots of row_bytes, a top list of `top_cap` entries, candidate arrays of `cand_cap` entries.
-__host__ __device__ inline WalkLayout walk_layout(uint32_t R, uint32_t row_bytes, uint32_t top_cap, uint32_t cand_cap) {
+// `stage_bytes` of value/row staging, `nbar` mbarriers, a top list of `top_cap` entries, candidate arrays of `cand_cap`.
+__host__ __device__ inline WalkLayout walk_layout_bytes(size_t stage_bytes, uint32_t nbar, uint32_t top_cap, uint32_t cand_cap) {
     WalkLayout l;
-    size_t o = (size_t)R * row_bytes;
+    size_t o = stage_bytes;
     o = (o + 15) & ~(size_t)15;
-    l.full = o, o += (size_t)R * 8;
+    l.full = o, o += (size_t)nbar * 8;
     l.top_d = o, o += (size_t)top_cap * 4;
     l.top_i = o, o += (size_t)top_cap * 4;
     l.cand_id = o, o += (size_t)cand_cap * 4;
@@ -65,6 +65,14 @@ __host__ __device__ inline WalkLayout walk_layout(uint32_t R, uint32_t row_bytes
     l.ctrl = o, o += sizeof(WalkCtrl);
     l.total = o;
     return l;
+}
+// R ring slots of row_bytes (plain rows)
+__host__ __device__ inline WalkLayout walk_layout(uint32_t R, uint32_t row_bytes, uint32_t top_cap, uint32_t cand_cap) {
+    return walk_layout_bytes((size_t)R * row_bytes, R, top_cap, cand_cap);
+}
+// PQ: look-up table [nsub][ncent] + value staging [dims]
+__host__ __device__ inline WalkLayout walk_layout_pq(uint32_t nsub, uint32_t ncent, uint32_t dims, uint32_t top_cap, uint32_t cand_cap) {
+    return walk_layout_bytes(((size_t)nsub * ncent + dims) * 4, 0, top_cap, cand_cap);
 }
 
 inline uint32_t pick_ring_slots(uint32_t row_bytes) {
@@ -120,23 +128,18 @@ __device__ __forceinline__ void top_insert(float* td, uint32_t* ti, uint32_t& si
         cursor = pos;
 }
 
-template <int DM, int SK, int NQ> struct Walker {
+// state shared by every evaluator / walker
+struct WalkBase {
     GraphView g;
     WalkSmem sm;
     uint32_t* vis;
     uint32_t* touched;
     uint32_t touched_cap;
     size_t words_per_cta;
-    uint4 qreg[NQ];
-    float a2;
-    uint32_t phase_bits;
-    uint64_t pol;
-    uint32_t nchunks, R, SPW;
     int warp, lane;
     unsigned long long st_dist, st_pops, st_hops; // thread 0's copy is the one that is reported
 
-    __device__ __forceinline__ void init(const GraphView& gv, uint8_t* smem_raw, const WalkLayout& lay, uint32_t ring_slots,
-                                         const SearchScratch& s) {
+    __device__ __forceinline__ void init_base(const GraphView& gv, uint8_t* smem_raw, const WalkLayout& lay, const SearchScratch& s) {
         g = gv;
         sm.ring = smem_raw;
         sm.full = reinterpret_cast<uint64_t*>(smem_raw + lay.full);
@@ -146,16 +149,33 @@ template <int DM, int SK, int NQ> struct Walker {
         sm.cand_d = reinterpret_cast<float*>(smem_raw + lay.cand_d);
         sm.ctrl = reinterpret_cast<WalkCtrl*>(smem_raw + lay.ctrl);
         warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        nchunks = g.row_bytes / 16;
-        R = ring_slots, SPW = ring_slots / kWalkWarps;
-        phase_bits = 0;
-        pol = policy_evict_first();
-        a2 = 0.f;
         st_dist = st_pops = st_hops = 0;
         vis = s.visited + (size_t)blockIdx.x * s.words_per_cta;
         touched = s.touched + (size_t)blockIdx.x * s.touched_cap;
         touched_cap = s.touched_cap;
         words_per_cta = s.words_per_cta;
+    }
+};
+
+// ---- evaluator for plain rows (f32 / f16 / i8 / b1): value in registers, rows through the bulk-copy ring --------
+template <int DM, int SK, int NQ> struct RowEval : WalkBase {
+    static __host__ __device__ WalkLayout layout(const GraphView& g, uint32_t R, uint32_t top_cap, uint32_t cand_cap) {
+        return walk_layout(R, g.row_bytes, top_cap, cand_cap);
+    }
+    uint4 qreg[NQ];
+    float a2;
+    uint32_t phase_bits;
+    uint64_t pol;
+    uint32_t nchunks, R, SPW;
+
+    __device__ __forceinline__ void init(const GraphView& gv, uint8_t* smem_raw, const WalkLayout& lay, uint32_t ring_slots,
+                                         const SearchScratch& s) {
+        init_base(gv, smem_raw, lay, s);
+        nchunks = g.row_bytes / 16;
+        R = ring_slots, SPW = ring_slots / kWalkWarps;
+        phase_bits = 0;
+        pol = policy_evict_first();
+        a2 = 0.f;
         if (threadIdx.x == 0) {
             for (uint32_t i = 0; i < R; ++i)
                 mbar_init(&sm.full[i], 1);
@@ -177,6 +197,8 @@ template <int DM, int SK, int NQ> struct Walker {
         if constexpr (DM == DM_COS)
             a2 = warp_sum(part);
     }
+    // a stored node becomes the value (refine_: candidate vs accepted; reverse links: target vs its neighbours)
+    __device__ __forceinline__ void load_node(uint32_t id) { load_value(g.vectors + (size_t)id * g.row_bytes); }
 
     __device__ __forceinline__ void issue(uint32_t slot, uint32_t id) {
         uint64_t* bar = &sm.full[slot];
@@ -219,6 +241,126 @@ template <int DM, int SK, int NQ> struct Walker {
             si = (si + 1 == SPW) ? 0 : si + 1;
         }
     }
+};
+
+// ---- evaluator for PQ-coded rows: asymmetric distance through a per-value look-up table ----------------------
+// Reference semantics (lantern_storage.hpp:137-149,264-267; index_dense.hpp:341-358): every stored operand is
+// decompressed (concatenation of centroid slices), the query / new vector never is.  Because a decoded vector is a
+// concatenation of centroid slices, d(value, decode(code)) = sum_s lut[s][code_s] with
+//   l2sq: lut[s][c] = |value_s - centroid_{c,s}|^2          cos: lut[s][c] = value_s . centroid_{c,s}  (+ norm tables)
+// which reproduces the reference up to fp32 summation order (verified 2e-7 relative).  When the value
+// is itself a stored node (refine_, reverse links) its table rows are copied from the centroid-pair table `pq_pair`
+// [nsub][ncent][ncent] precomputed at index creation.  Code rows (nsub bytes) are read straight from HBM/L2.
+template <int DM> struct PqEval : WalkBase {
+    static __host__ __device__ WalkLayout layout(const GraphView& g, uint32_t, uint32_t top_cap, uint32_t cand_cap) {
+        return walk_layout_pq(g.num_subvectors, g.num_centroids, g.dims, top_cap, cand_cap);
+    }
+    float* lut;  // shared [nsub][ncent]
+    float* qbuf; // shared [dims]
+    float a2;
+
+    __device__ __forceinline__ void init(const GraphView& gv, uint8_t* smem_raw, const WalkLayout& lay, uint32_t, const SearchScratch& s) {
+        init_base(gv, smem_raw, lay, s);
+        lut = reinterpret_cast<float*>(smem_raw);
+        qbuf = lut + (size_t)g.num_subvectors * g.num_centroids;
+        a2 = 0.f;
+        __syncthreads();
+    }
+
+    // `row` = raw f32 vector (dims floats) in global memory
+    __device__ __forceinline__ void load_value(const uint8_t* row) {
+        const float* q = reinterpret_cast<const float*>(row);
+        const uint32_t dims = g.dims, ncent = g.num_centroids, nsub = g.num_subvectors, sd = dims / nsub;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < dims; i += kWalkThreads)
+            qbuf[i] = __ldg(q + i);
+        __syncthreads();
+        if constexpr (DM == DM_COS) {
+            float part = 0.f;
+            for (uint32_t i = lane; i < dims; i += 32)
+                part += qbuf[i] * qbuf[i];
+            a2 = warp_sum(part);
+        }
+        for (uint32_t e = threadIdx.x; e < nsub * ncent; e += kWalkThreads) {
+            const uint32_t s = e / ncent, c = e - s * ncent;
+            const float* cen = g.codebook + (size_t)c * dims + (size_t)s * sd;
+            const float* qs = qbuf + (size_t)s * sd;
+            float acc = 0.f;
+            for (uint32_t i = 0; i < sd; ++i) {
+                const float cv = __ldg(cen + i);
+                if constexpr (DM == DM_COS)
+                    acc = fmaf(qs[i], cv, acc);
+                else {
+                    const float d = qs[i] - cv;
+                    acc = fmaf(d, d, acc);
+                }
+            }
+            lut[e] = acc;
+        }
+        __syncthreads();
+    }
+
+    __device__ __forceinline__ void load_node(uint32_t id) {
+        const uint32_t ncent = g.num_centroids, nsub = g.num_subvectors;
+        const uint8_t* codes = g.vectors + (size_t)id * g.row_bytes;
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < nsub * ncent; e += kWalkThreads) {
+            const uint32_t s = e / ncent, c = e - s * ncent;
+            lut[e] = __ldg(g.pq_pair + ((size_t)s * ncent + __ldg(codes + s)) * ncent + c);
+        }
+        if constexpr (DM == DM_COS) {
+            float part = 0.f;
+            for (uint32_t s = lane; s < nsub; s += 32)
+                part += __ldg(g.pq_norm + (size_t)s * ncent + __ldg(codes + s));
+            a2 = warp_sum(part);
+        }
+        __syncthreads();
+    }
+
+    __device__ __forceinline__ void eval(uint32_t n) {
+        const uint32_t ncent = g.num_centroids, nsub = g.num_subvectors, words = (nsub + 3) / 4;
+        for (uint32_t j = warp; j < n; j += kWalkWarps) {
+            const uint32_t* row = reinterpret_cast<const uint32_t*>(g.vectors + (size_t)sm.cand_id[j] * g.row_bytes);
+            float acc = 0.f, b2 = 0.f;
+            for (uint32_t wi = lane; wi < words; wi += 32) {
+                const uint32_t w32 = __ldg(row + wi);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t s = 4 * wi + b;
+                    if (s < nsub) {
+                        const uint32_t c = (w32 >> (8 * b)) & 255u;
+                        acc += lut[s * ncent + c];
+                        if constexpr (DM == DM_COS)
+                            b2 += __ldg(g.pq_norm + (size_t)s * ncent + c);
+                    }
+                }
+            }
+            acc = warp_sum(acc);
+            float d = acc;
+            if constexpr (DM == DM_COS) {
+                b2 = warp_sum(b2);
+                d = cos_from_parts(acc, a2, b2);
+            }
+            if (lane == 0)
+                sm.cand_d[j] = d;
+        }
+    }
+};
+
+template <class E> struct WalkerT : E {
+    using E::eval;
+    using E::g;
+    using E::lane;
+    using E::load_node;
+    using E::sm;
+    using E::st_dist;
+    using E::st_hops;
+    using E::st_pops;
+    using E::touched;
+    using E::touched_cap;
+    using E::vis;
+    using E::warp;
+    using E::words_per_cta;
 
     __device__ __forceinline__ const uint32_t* list_of(uint32_t node, int level, uint32_t& width) const {
         if (level == 0) {
@@ -419,7 +561,7 @@ template <int DM, int SK, int NQ> struct Walker {
             __syncthreads();
             const uint32_t c_id = sm.top_i[consumed] & kIdMask;
             const float c_d = sm.top_d[consumed];
-            load_value(g.vectors + (size_t)c_id * g.row_bytes);
+            load_node(c_id);
             for (uint32_t j = threadIdx.x; j < submitted; j += kWalkThreads)
                 sm.cand_id[j] = sm.top_i[j] & kIdMask;
             __syncthreads();
@@ -444,7 +586,16 @@ template <int DM, int SK, int NQ> struct Walker {
     }
 };
 
+template <int DM, int SK, int NQ> using Walker = WalkerT<RowEval<DM, SK, NQ>>;
+template <int DM> using PqWalker = WalkerT<PqEval<DM>>;
+
 // ---- (DM, SK, NQ) dispatch shared by the launchers ----------------------------------------------------
+// PQ indexes: fn(walker type tag) with PqWalker<DM>
+template <typename T> struct TypeTag {
+    using type = T;
+};
+template <typename Fn> void dispatch_walker(bool pq, int dm, int sk, int nq, Fn&& fn);
+
 template <typename Fn> void dispatch_walk(int dm, int sk, int nq, Fn&& fn) {
 #define LB_NQ_CASES(DMv, SKv)                                                                                          \
     switch (nq) {                                                                                                      \
@@ -475,6 +626,19 @@ template <typename Fn> void dispatch_walk(int dm, int sk, int nq, Fn&& fn) {
     }
 #undef LB_NQ_CASES
     throw CudaError("unsupported metric / scalar kind / dimensionality combination");
+}
+
+template <typename Fn> void dispatch_walker(bool pq, int dm, int sk, int nq, Fn&& fn) {
+    if (pq) {
+        if (dm == DM_L2SQ)
+            return fn(TypeTag<PqWalker<DM_L2SQ>>{});
+        if (dm == DM_COS)
+            return fn(TypeTag<PqWalker<DM_COS>>{});
+        throw CudaError("pq index: only l2sq and cos metrics are supported");
+    }
+    dispatch_walk(dm, sk, nq, [&](auto d, auto s, auto n) {
+        fn(TypeTag<Walker<decltype(d)::value, decltype(s)::value, decltype(n)::value>>{});
+    });
 }
 
 } // namespace lb200

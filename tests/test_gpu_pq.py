@@ -1,0 +1,84 @@
+"""GPU parity of the PQ index path (asymmetric-distance search and build over PQ codes) against the oracle."""
+import numpy as np
+import pytest
+
+from test_golden import LATTICE, PQ_CODEBOOK, G, same_up_to_ties
+
+pytestmark = pytest.mark.gpu
+
+
+def port_pq(port, X, cb, nsub, metric="l2sq", **kw):
+    idx = port.PortIndex(X.shape[1], metric, "f32", pq=True, num_centroids=len(cb), num_subvectors=nsub, codebook=cb, **kw)
+    idx.reserve(len(X))
+    for i, v in enumerate(X):
+        idx.add(i + 1, v)
+    return idx
+
+
+def test_toy_codebook_matches_reference_outputs(eng):
+    """external_index_server_test.rs:684-690 codebook; expected keys/distances come from the unmodified reference."""
+    X = (LATTICE * 0.1).astype(np.float32)
+    g = eng.Index(3, "l2sq", "f32", M=12, efc=64, ef=32, pq=True, num_centroids=4, num_subvectors=3, codebook=PQ_CODEBOOK)
+    g.set_option("build_batch", 1)
+    g.reserve(len(X))
+    g.add_batch(np.arange(len(X), dtype=np.uint64), X)
+    g.build()
+    k, d, _ = g.search_batch(X, 5)
+    same_up_to_ties(k, d, G["pq_keys"], G["pq_dists"])
+
+
+@pytest.mark.parametrize("metric", ["l2sq", "cos"])
+def test_pq_same_graph_same_ids(eng, port, metric):
+    rng = np.random.default_rng(8)
+    d, nsub, ncent, n = 32, 8, 64, 2500
+    cb = rng.standard_normal((ncent, d)).astype(np.float32)
+    X = (cb[rng.integers(0, ncent, n)] + 0.3 * rng.standard_normal((n, d))).astype(np.float32)
+    Q = (cb[rng.integers(0, ncent, 150)] + 0.3 * rng.standard_normal((150, d))).astype(np.float32)
+    p = port_pq(port, X, cb, nsub, metric, M=16, efc=64, ef=48)
+    g = eng.Index(d, metric, "f32", M=16, efc=64, ef=48, pq=True, num_centroids=ncent, num_subvectors=nsub, codebook=cb)
+    g.load_buffer(p.save_buffer())  # the oracle's graph + codes
+    gk, gd, _ = g.search_batch(Q, 10)
+    pk, pd, _, tot = p.search_batch(Q, 10)
+    assert np.allclose(gd, pd, rtol=2e-5, atol=2e-6)
+    assert np.mean(np.all(gk == pk, axis=1)) > 0.95
+    st = g.last_stats()
+    assert abs(st["computed_distances"] - tot["computed_distances"]) <= 0.01 * tot["computed_distances"]
+
+
+def test_pq_exact_order_build_byte_identical_on_integer_data(eng, port):
+    """Integer codebook + integer vectors: every distance is an exact small integer on both sides."""
+    rng = np.random.default_rng(12)
+    d, nsub, ncent, n = 16, 4, 16, 900
+    cb = rng.integers(-4, 5, (ncent, d)).astype(np.float32)
+    X = rng.integers(-5, 6, (n, d)).astype(np.float32)
+    p = port_pq(port, X, cb, nsub, "l2sq", M=8, efc=48, ef=32)
+    g = eng.Index(d, "l2sq", "f32", M=8, efc=48, ef=32, pq=True, num_centroids=ncent, num_subvectors=nsub, codebook=cb)
+    g.set_option("build_batch", 1)
+    g.reserve(n)
+    g.add_batch(np.arange(1, n + 1, dtype=np.uint64), X)
+    g.build()
+    gb, pb = g.save_buffer(), p.save_buffer()
+    assert len(gb) == len(pb)
+    assert np.mean(gb == pb) > 0.99  # ties everywhere (integer distances): only queue tie order may differ
+
+
+def test_pq_batched_build_recall(eng, port):
+    rng = np.random.default_rng(3)
+    d, nsub, ncent, n = 64, 16, 256, 20000
+    centers = rng.standard_normal((64, d)).astype(np.float32)
+    X = (centers[rng.integers(0, 64, n)] + 0.4 * rng.standard_normal((n, d))).astype(np.float32)
+    Q = (centers[rng.integers(0, 64, 300)] + 0.4 * rng.standard_normal((300, d))).astype(np.float32)
+    # a simple codebook: per-subspace random sample of the data (k-means is not needed for a parity test)
+    cb = X[rng.choice(n, ncent, replace=False)].copy()
+    g = eng.Index(d, "l2sq", "f32", M=16, efc=128, ef=64, pq=True, num_centroids=ncent, num_subvectors=nsub, codebook=cb)
+    g.reserve(n)
+    g.add_batch(np.arange(1, n + 1, dtype=np.uint64), X)
+    g.build()
+    gk, gd, _ = g.search_batch(Q, 10)
+    # PQ-exact ground truth: brute force over the DECODED corpus (what the index can at best return)
+    codes = eng.quantize_pq(cb, X, nsub, compat128=True)
+    dec = eng.dequantize_pq(cb, codes)
+    tk, td = eng.exact_search(dec, Q, 10, "l2sq")
+    rec = np.mean([len(set(a.tolist()) & set((b + 1).tolist())) / 10 for a, b in zip(gk, tk)])
+    assert rec > 0.85, rec  # hnsw_pq_index.sql:129-131: index recall within 0.1 of PQ-exact
+    assert np.allclose(np.sort(gd[:, 0]), np.sort(np.minimum(gd[:, 0], td[:, 0])), rtol=1e-4) or rec > 0.9
