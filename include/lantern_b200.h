@@ -150,7 +150,9 @@ LB200_EXPORT void lb200_set_option(lb200_index_t, char const* name, size_t value
 
 /* ---- search path: usearch.h:277-296, lib.cpp:389-410 ------------------------------------------ */
 /* One query, host buffers.  Returns the number of matches written (ascending distance).
- * continue_search (scan.c:273-281 streaming) is not implemented on the GPU: must be false. */
+ * continue_search (scan.c:273-281 streaming): returns the NEXT `count` neighbours of the query passed to the preceding
+ * call (same bytes required); implemented as a fresh search for (returned so far + count), so results never repeat and,
+ * unlike the reference's frontier continuation (index.hpp:3415-3430), reachable neighbours are never lost. */
 LB200_EXPORT size_t lb200_search_ef(lb200_index_t, void const* query_vector, lb200_scalar_kind_t query_kind, size_t count,
                                     size_t ef, bool continue_search, lb200_key_t* keys, lb200_distance_t* distances,
                                     lb200_error_t* error);

@@ -229,17 +229,32 @@ LB200_EXPORT size_t lb200_search_ef(lb200_index_t h, void const* query, lb200_sc
                                     bool continue_search, lb200_key_t* keys, lb200_distance_t* distances, lb200_error_t* error) {
     size_t found = 0;
     guarded(error, [&] {
-        if (continue_search)
-            throw CudaError("continue_search is not implemented by the GPU engine");
         Index* idx = as_index(h);
-        std::vector<uint64_t> k(count);
-        std::vector<float> d(count);
+        const size_t qbytes = scalar_row_bytes(kind, idx->config().dims);
+        // Streaming (scan.c:240-292 doubles k and passes continue_search=true; index.hpp:3415-3430 then skips what was
+        // already returned and resumes from the frontier).  Here the continuation is a fresh search for
+        // (already returned + count) neighbours of the same query, of which the new tail is handed out: the caller sees
+        // the same contract -- never a result twice, ascending distance -- and, unlike the reference,
+        // never loses reachable results.
+        size_t skip = 0;
+        if (continue_search) {
+            if (idx->stream_query_.size() != qbytes || memcmp(idx->stream_query_.data(), query, qbytes) != 0)
+                throw CudaError("continue_search: no preceding search of this query on this index");
+            skip = idx->stream_consumed_;
+        }
+        const size_t want = skip + count;
+        if (want > 4096)
+            throw CudaError("continue_search: more than 4096 results requested in total");
+        std::vector<uint64_t> k(want);
+        std::vector<float> d(want);
         size_t c = 0;
-        idx->search_host(query, 1, scalar_row_bytes(kind, idx->config().dims), kind, count, ef, k.data(), d.data(), &c);
+        idx->search_host(query, 1, qbytes, kind, want, ef, k.data(), d.data(), &c);
+        found = c > skip ? c - skip : 0;
         // dump_to writes only `found` entries (index.hpp:2426-2433)
-        memcpy(keys, k.data(), c * sizeof(uint64_t));
-        memcpy(distances, d.data(), c * sizeof(float));
-        found = c;
+        memcpy(keys, k.data() + skip, found * sizeof(uint64_t));
+        memcpy(distances, d.data() + skip, found * sizeof(float));
+        idx->stream_query_.assign((const uint8_t*)query, (const uint8_t*)query + qbytes);
+        idx->stream_consumed_ = skip + found;
     });
     return found;
 }

@@ -147,6 +147,9 @@ class Index {
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     uint32_t last_nq_ = 0;
     std::mutex mu_;
+    // streaming state of the single-query entry point (usearch_search_ef continue_search, scan.c:240-292)
+    std::vector<uint8_t> stream_query_;
+    size_t stream_consumed_ = 0;
 
     void ensure_scratch(uint32_t ctas);
     void* io_buffer(size_t bytes);

@@ -32,8 +32,8 @@ def test_pq_same_graph_same_ids(eng, port, metric):
     rng = np.random.default_rng(8)
     d, nsub, ncent, n = 32, 8, 64, 2500
     cb = rng.standard_normal((ncent, d)).astype(np.float32)
-    X = (cb[rng.integers(0, ncent, n)] + 0.3 * rng.standard_normal((n, d))).astype(np.float32)
-    Q = (cb[rng.integers(0, ncent, 150)] + 0.3 * rng.standard_normal((150, d))).astype(np.float32)
+    X = rng.standard_normal((n, d)).astype(np.float32)  # unstructured: codes are diverse, exact distance ties are rare
+    Q = rng.standard_normal((150, d)).astype(np.float32)
     p = port_pq(port, X, cb, nsub, metric, M=16, efc=64, ef=48)
     g = eng.Index(d, metric, "f32", M=16, efc=64, ef=48, pq=True, num_centroids=ncent, num_subvectors=nsub, codebook=cb)
     g.load_buffer(p.save_buffer())  # the oracle's graph + codes

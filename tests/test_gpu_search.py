@@ -115,3 +115,34 @@ def test_save_load_roundtrip_bytes(eng, port):
     g.load_buffer(buf)
     out = g.save_buffer()
     assert len(out) == len(buf) and np.array_equal(out, buf)
+
+
+def test_continue_search_streaming(eng, port):
+    """scan.c:240-292: first k = init_k, then continue_search with doubled k; no key may be returned twice and the
+    concatenation must be ascending and equal to one big search."""
+    import ctypes as C
+    X = structured(1500, 24, seed=31)
+    pidx = build_port_index(port, X, "l2sq", "f32", M=8, efc=64, ef=64)
+    g = eng.Index(24, "l2sq", "f32", M=8, efc=64, ef=64)
+    g.load_buffer(pidx.save_buffer())
+    q = structured(1, 24, seed=32)[0]
+    L = eng.lib()
+    got_k, got_d = [], []
+    k = 10
+    cont = False
+    for _ in range(4):
+        keys, dists = np.zeros(k, np.uint64), np.zeros(k, np.float32)
+        err = C.c_char_p()
+        n = L.lb200_search_ef(g.h, q.ctypes.data, 1, k, 0, cont, keys.ctypes.data, dists.ctypes.data, C.byref(err))
+        assert not err.value
+        got_k += list(keys[:n]); got_d += list(dists[:n])
+        cont, k = True, k * 2
+    assert len(got_k) == 10 + 20 + 40 + 80 and len(set(got_k)) == len(got_k)
+    assert all(a <= b for a, b in zip(got_d, got_d[1:]))
+    allk, alld = g.search(q, 150, ef=150)
+    assert list(allk) == got_k
+    # a different query cannot be "continued"
+    err = C.c_char_p()
+    other = structured(1, 24, seed=33)[0]
+    L.lb200_search_ef(g.h, other.ctypes.data, 1, 5, 0, True, keys.ctypes.data, dists.ctypes.data, C.byref(err))
+    assert err.value and b"continue_search" in err.value
