@@ -43,6 +43,10 @@ WORKLOADS = {
                   desc="cfg2s (smoke-size): 100k x d768 f32 l2sq, M=16 efc=128 ef=64, batch-1024 k=10"),
     "cfg3": dict(n=10_000_000, dim=768, metric="cos", M=32, efc=128, ef=128, batch=4096, k=10,
                  desc="cfg3: 10M x d768 f32 cosine, M=32 efc=128 ef=128, batch-4096 k=10"),
+    "cfg4": dict(n=10_000_000, dim=1536, metric="l2sq", M=16, efc=128, ef=64, batch=4096, k=100, pq=(96, 256),
+                 desc="cfg4: 10M x d1536 f32 -> PQ 96 subvectors x 256 centroids, l2sq, M=16 efc=128 ef=64 (expansion 100), batch-4096 k=100"),
+    "cfg4s": dict(n=1_000_000, dim=1536, metric="l2sq", M=16, efc=128, ef=64, batch=4096, k=100, pq=(96, 256),
+                  desc="cfg4s (1/10 scale): 1M x d1536 f32 -> PQ 96x256, l2sq, M=16 efc=128 ef=64 (expansion 100), batch-4096 k=100"),
     # BASELINE configs[4] is 50M x 768-byte binary vectors over 8 GPUs: one shard's worth (6.25M) on one GPU
     "cfg5s": dict(n=6_250_000, dim=6144, kind="b1", metric="hamming", M=16, efc=128, ef=64, batch=4096, k=10,
                   desc="cfg5s (one of 8 shards of cfg5): 6.25M x 6144-bit (768 B) hamming, M=16 efc=128 ef=64, batch-4096 k=10"),
@@ -192,7 +196,12 @@ def run_reference(args, wl):
     nsteps = args.steps + args.warmup
     pool = min(nsteps, args.query_pool)
     Q = gen(pool * wl["batch"], wl["dim"], SEED_QUERY)
-    idx = reflib.RefIndex(wl["dim"], wl["metric"], wl.get("kind", "f32"), M=wl["M"], efc=wl["efc"], ef=wl["ef"], threads=cores)
+    pqkw = {}
+    if wl.get("pq"):  # codebook for the reference arm: 256 corpus rows (a valid, if untrained, codebook), stated in `sample`
+        nsub, ncent = wl["pq"]
+        pqkw = dict(pq=True, num_centroids=ncent, num_subvectors=nsub,
+                    codebook=X[np.random.default_rng(7).choice(len(X), ncent, replace=False)].copy())
+    idx = reflib.RefIndex(wl["dim"], wl["metric"], wl.get("kind", "f32"), M=wl["M"], efc=wl["efc"], ef=wl["ef"], threads=cores, **pqkw)
     idx.reserve(len(X))
     keys = np.arange(1, len(X) + 1, dtype=np.uint64)
     t0 = time.perf_counter()
@@ -260,23 +269,68 @@ def run_ours(args, wl):
 
     # ---- corpus shard of this rank: contiguous row range ----
     lo, hi = (n * rank) // world, (n * (rank + 1)) // world
-    t0 = time.perf_counter()
-    X = gen_t(n, dim, SEED_CORPUS, dev)[lo:hi].contiguous() if world > 1 else gen_t(n, dim, SEED_CORPUS, dev)
-    Q = gen_t(pool * B, dim, SEED_QUERY, dev)
-    torch.cuda.synchronize()
-    t_gen = time.perf_counter() - t0
-
-    ef_shard = args.shard_ef if (world > 1 and args.shard_ef > 0) else ef
-    idx = api.Index(dim, wl["metric"], kind, M=wl["M"], efc=wl["efc"], ef=ef)
-    idx.reserve(hi - lo)
-    keys_host = np.arange(lo + 1, hi + 1, dtype=np.uint64)  # global keys = row + 1
-    t0 = time.perf_counter()
-    idx.add_batch_device(keys_host, X.data_ptr(), hi - lo, rowb, kind)
-    idx.build()
-    torch.cuda.synchronize()
-    t_build = time.perf_counter() - t0
-
+    pq = wl.get("pq")
     stream = torch.cuda.current_stream()
+    nrec = min(B, 1024)
+    t0 = time.perf_counter()
+    Q = gen_t(pool * B, dim, SEED_QUERY, dev)
+    ef_shard = args.shard_ef if (world > 1 and args.shard_ef > 0) else ef
+    pq_info = None
+    if not pq:
+        X = gen_t(n, dim, SEED_CORPUS, dev)[lo:hi].contiguous() if world > 1 else gen_t(n, dim, SEED_CORPUS, dev)
+        torch.cuda.synchronize()
+        t_gen = time.perf_counter() - t0
+        idx = api.Index(dim, wl["metric"], kind, M=wl["M"], efc=wl["efc"], ef=ef)
+        idx.reserve(hi - lo)
+        keys_host = np.arange(lo + 1, hi + 1, dtype=np.uint64)  # global keys = row + 1
+        t0 = time.perf_counter()
+        idx.add_batch_device(keys_host, X.data_ptr(), hi - lo, rowb, kind)
+        idx.build()
+        torch.cuda.synchronize()
+        t_build = time.perf_counter() - t0
+    else:
+        # PQ storage (cfg4): the raw fp32 corpus (61 GB at 10M x d1536) is never resident as a whole: it is generated
+        # chunk by chunk; each chunk feeds (a) the running exact top-k used as recall ground truth, (b) lb200_add_batch +
+        # lb200_build (PQ encode + insertion), and is then dropped.  The codebook is trained once by the engine's own
+        # k-means (lb200_train_pq_device) on the first 200k rows and given to both sides.
+        assert world == 1, "PQ workloads run on one GPU"
+        nsub, ncent = pq
+        chunk = 500_000
+        sample = gen_t(min(n, 200_000), dim, SEED_CORPUS * 1000, dev)
+        t1 = time.perf_counter()
+        codebook, rounds = api.train_pq_device(sample.data_ptr(), dim * 4, len(sample), dim, nsub, ncent, wl["metric"], 15, 7)
+        t_train = time.perf_counter() - t1
+        del sample
+        idx = api.Index(dim, wl["metric"], "f32", M=wl["M"], efc=wl["efc"], ef=ef, pq=True, num_centroids=ncent,
+                        num_subvectors=nsub, codebook=codebook)
+        idx.reserve(n)
+        run_k = torch.full((2, nrec, k), -1, dtype=torch.int64, device=dev)
+        run_d = torch.full((2, nrec, k), float("inf"), dtype=torch.float32, device=dev)
+        t_gen, t_build = 0.0, 0.0
+        for c, clo in enumerate(range(0, n, chunk)):
+            chi = min(n, clo + chunk)
+            t1 = time.perf_counter()
+            Xc = gen_t(chi - clo, dim, SEED_CORPUS * 1000 + c, dev)
+            torch.cuda.synchronize()
+            t_gen += time.perf_counter() - t1
+            api.exact_search_device(Xc.data_ptr(), chi - clo, rowb, Q.data_ptr(), nrec, rowb, k, run_k[1].data_ptr(),
+                                    run_d[1].data_ptr(), wl["metric"], "f32", dim, stream.cuda_stream)
+            run_k[1] += clo + 1
+            mk = torch.empty((nrec, k), dtype=torch.int64, device=dev)
+            md = torch.empty((nrec, k), dtype=torch.float32, device=dev)
+            api.merge_shards_device(run_k.data_ptr(), run_d.data_ptr(), 2, nrec, k, mk.data_ptr(), md.data_ptr(), stream.cuda_stream)
+            run_k[0], run_d[0] = mk, md
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            idx.add_batch_device(np.arange(clo + 1, chi + 1, dtype=np.uint64), Xc.data_ptr(), chi - clo, rowb, "f32")
+            idx.build()
+            torch.cuda.synchronize()
+            t_build += time.perf_counter() - t1
+            del Xc
+        pq_truth = run_k[0].cpu().numpy()
+        pq_info = {"num_subvectors": nsub, "num_centroids": ncent, "kmeans_rounds": rounds, "kmeans_seconds": t_train,
+                   "codebook": "trained by lb200_train_pq_device on 200k rows, compat128 encode (reference quirk)"}
+
     out_keys = torch.empty((B, k), dtype=torch.int64, device=dev)
     out_dists = torch.empty((B, k), dtype=torch.float32, device=dev)
     out_counts = torch.empty((B,), dtype=torch.int32, device=dev)
@@ -306,12 +360,12 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
     # ---- ground truth for recall (untimed): brute force on this rank's shard, merged like the search results ----
-    nrec = min(B, 1024)
     tk = torch.empty((nrec, k), dtype=torch.int64, device=dev)
     td = torch.empty((nrec, k), dtype=torch.float32, device=dev)
-    api.exact_search_device(X.data_ptr(), hi - lo, rowb, Q.data_ptr(), nrec, rowb, k, tk.data_ptr(), td.data_ptr(),
-                            wl["metric"], kind, dim, stream.cuda_stream)
-    tk += lo + 1  # offsets -> global keys
+    if not pq:
+        api.exact_search_device(X.data_ptr(), hi - lo, rowb, Q.data_ptr(), nrec, rowb, k, tk.data_ptr(), td.data_ptr(),
+                                wl["metric"], kind, dim, stream.cuda_stream)
+        tk += lo + 1  # offsets -> global keys
     if world > 1:
         gk = torch.empty((world, nrec, k), dtype=torch.int64, device=dev)
         gd = torch.empty((world, nrec, k), dtype=torch.float32, device=dev)
@@ -322,7 +376,7 @@ def run_ours(args, wl):
         api.merge_shards_device(gk.data_ptr(), gd.data_ptr(), world, nrec, k, tk2.data_ptr(), td2.data_ptr(), stream.cuda_stream)
         tk = tk2
     torch.cuda.synchronize()
-    truth = tk.cpu().numpy()
+    truth = pq_truth if pq else tk.cpu().numpy()
 
     # ---- multi-GPU: per-shard beam width.  Every query visits every shard, so throughput only grows
     #      if the per-shard beam shrinks: pick the smallest ef_s >= k whose MERGED recall@10 reaches the recall of
@@ -437,7 +491,7 @@ def run_ours(args, wl):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": "hnsw_search_kernel<%s,%s>" % (wl["metric"], kind),
+                "peak_source": peak_src, "kernel": "hnsw_search_kernel<%s,%s>" % (wl["metric"], "pq" if pq else kind),
                 "kernel_ms_per_step": kern_ms / args.steps, "algorithmic_bytes_per_step": alg_bytes / args.steps,
                 "dist_evals_per_query": n_dist / (args.steps * B), "pops_per_query": pops / (args.steps * B)}
 
@@ -495,7 +549,33 @@ def run_ours(args, wl):
 
     # ---- CPU baseline (rank 0, N=1): the unmodified reference on the host cores over the SAME index file ----
     cpu_baseline, parity = None, None
-    if world == 1 and not args.no_cpu_baseline and n * rowb <= 8e9:  # the reference needs the index file twice in host RAM
+    if world == 1 and not args.no_cpu_baseline and pq:
+        # the reference refuses to LOAD pq index files (lantern_storage.hpp:550-551), so it builds its own pq graph, with
+        # the same codebook, over a bounded prefix of the corpus and searches the bench's query batches
+        from oracle import reflib
+        if reflib.available():
+            cores = reflib.lib().refx_hardware_threads()
+            n_ref = min(n, args.pq_ref_rows)
+            Xr = gen_t(n_ref, dim, SEED_CORPUS * 1000, dev).cpu().numpy()
+            ridx = reflib.RefIndex(dim, wl["metric"], M=wl["M"], efc=wl["efc"], ef=ef, threads=cores, pq=True,
+                                   num_centroids=pq[1], num_subvectors=pq[0], codebook=codebook)
+            ridx.reserve(n_ref)
+            t0 = time.perf_counter()
+            ridx.add_batch(np.arange(1, n_ref + 1, dtype=np.uint64), Xr, threads=cores)
+            t_rb = time.perf_counter() - t0
+            qh = Q.cpu().numpy()
+            spent, done, s = 0.0, 0, 0
+            while spent < args.cpu_seconds and s < pool:
+                t0 = time.perf_counter()
+                ridx.search_batch(qh[s * B:(s + 1) * B], k, threads=cores)
+                spent += time.perf_counter() - t0
+                done += B
+                s += 1
+            cpu_baseline = {"value": done / spent, "unit": "queries/s", "cores": cores, "kind": "reference",
+                            "sample": "unmodified usearch (oracle/_ref) builds its own pq graph over the first %d of %d rows (%.0f s) "
+                                      "with the same codebook and searches %d queries (%.1f s) on %d threads" % (
+                                          n_ref, n, t_rb, done, spent, cores)}
+    if world == 1 and not args.no_cpu_baseline and not pq and n * rowb <= 8e9:  # the reference needs the index file twice in host RAM
         from oracle import reflib
         if reflib.available():
             cores = reflib.lib().refx_hardware_threads()
@@ -548,7 +628,7 @@ def run_ours(args, wl):
                        "generator": ("64 random prototypes XOR 10%% bit flips, seeds %d/%d/%d" % (SEED_P, SEED_CORPUS, SEED_QUERY)) if kind == "b1" else
                        "x = z P + %.2f eps, z~N(0,I_%d), seeds %d/%d/%d" % (NOISE, LATENT, SEED_P, SEED_CORPUS, SEED_QUERY)},
             "recall_at_10": rec, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "parity": parity, "sharding": shard_info,
+            "cpu_baseline": cpu_baseline, "parity": parity, "sharding": shard_info, "pq": pq_info,
             "build": {"vectors_per_s": (hi - lo) / t_build, "seconds": t_build, "datagen_seconds": t_gen},
         }
         print(json.dumps(line))
@@ -569,6 +649,7 @@ def main():
                          "1-GPU recall at the workload's ef), -1 = same ef as the workload")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="bound on the cpu_baseline search time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pq-ref-rows", type=int, default=100_000, help="pq workloads: rows the reference indexes for cpu_baseline")
     ap.add_argument("--ref-seconds", type=float, default=60.0, help="--impl reference: target duration of the K timed steps")
     ap.add_argument("--ref-build-seconds", type=float, default=75.0, help="--impl reference: budget for the reference's own build")
     ap.add_argument("--ref-rows", type=int, default=0, help="--impl reference: corpus prefix to index (0 = auto by core count)")

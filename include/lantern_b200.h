@@ -219,6 +219,18 @@ LB200_EXPORT void lb200_quantize_pq(float const* codebook, size_t dims, size_t n
 LB200_EXPORT void lb200_dequantize_pq(float const* codebook, size_t dims, size_t num_centroids, size_t num_subvectors,
                                       uint8_t const* codes, size_t count, float* vectors, lb200_error_t* error);
 
+/* PQ codebook training (lantern_hnsw/src/hnsw/product_quantization.c:207-293 semantics: one k-means per subvector,
+ * random distinct rows as initial centres, Lloyd rounds until the mean centre shift is <= 0.1 or `max_iter` rounds).
+ * vectors: float[count][dims] in host memory; codebook out: float[num_centroids][dims].  init_rows (may be NULL):
+ * uint32[num_subvectors][num_centroids] row indices to start from (for reproducible runs).  Returns rounds executed. */
+LB200_EXPORT int lb200_train_pq(float const* vectors, size_t count, size_t dims, size_t num_subvectors, size_t num_centroids,
+                                lb200_metric_kind_t metric_kind, size_t max_iter, uint64_t seed, uint32_t const* init_rows,
+                                float* codebook, lb200_error_t* error);
+/* Same with the training vectors resident in device memory (`stride` bytes apart); codebook still returned to the host. */
+LB200_EXPORT int lb200_train_pq_device(void const* d_vectors, size_t stride, size_t count, size_t dims, size_t num_subvectors,
+                                       size_t num_centroids, lb200_metric_kind_t metric_kind, size_t max_iter, uint64_t seed,
+                                       uint32_t const* init_rows, float* codebook, lb200_error_t* error);
+
 /* ---- multi-GPU epilogue: merge G per-shard top-k lists (already all-gathered) per query ---------- */
 /* d_keys/d_dists: [G][nq][count] on this device; outputs [nq][count]. */
 LB200_EXPORT void lb200_merge_shards_device(lb200_key_t const* d_keys, lb200_distance_t const* d_dists, size_t shards,

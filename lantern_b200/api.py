@@ -108,6 +108,10 @@ SIGNATURES = {
                                  C.c_int, ERRP]),
     "lb200_dequantize_pq": (None, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
                                    ERRP]),
+    "lb200_train_pq": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_uint64,
+                                 C.c_void_p, C.c_void_p, ERRP]),
+    "lb200_train_pq_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
+                                        C.c_size_t, C.c_uint64, C.c_void_p, C.c_void_p, ERRP]),
     "lb200_merge_shards_device": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p,
                                          C.c_void_p, C.c_void_p, ERRP]),
     "lb200_device_count": (C.c_int, []),
@@ -337,6 +341,23 @@ def dequantize_pq(codebook, codes):
     out = np.zeros((len(c2), cb.shape[1]), np.float32)
     _static("lb200_dequantize_pq", _ptr(cb), cb.shape[1], cb.shape[0], c2.shape[1], _ptr(c2), len(c2), _ptr(out))
     return out
+
+
+def train_pq(vectors, num_subvectors, num_centroids, metric="l2sq", max_iter=20, seed=1, init_rows=None):
+    """k-means codebook float[num_centroids][dims] (product_quantization.c semantics); returns (codebook, rounds)."""
+    v = np.ascontiguousarray(vectors, dtype=np.float32)
+    cb = np.zeros((num_centroids, v.shape[1]), np.float32)
+    ir = None if init_rows is None else np.ascontiguousarray(init_rows, dtype=np.uint32)
+    rounds = _static("lb200_train_pq", _ptr(v), len(v), v.shape[1], num_subvectors, num_centroids, METRIC[metric], max_iter, seed,
+                     _ptr(ir), _ptr(cb))
+    return cb, rounds
+
+
+def train_pq_device(d_ptr, stride, count, dims, num_subvectors, num_centroids, metric="l2sq", max_iter=20, seed=1):
+    cb = np.zeros((num_centroids, dims), np.float32)
+    rounds = _static("lb200_train_pq_device", C.c_void_p(d_ptr), stride, count, dims, num_subvectors, num_centroids, METRIC[metric],
+                     max_iter, seed, None, _ptr(cb))
+    return cb, rounds
 
 
 def merge_shards_device(d_keys, d_dists, shards, nq, k, d_out_keys, d_out_dists, stream=0):

@@ -527,6 +527,43 @@ LB200_EXPORT void lb200_dequantize_pq(float const* codebook, size_t dims, size_t
     });
 }
 
+LB200_EXPORT int lb200_train_pq_device(void const* d_vectors, size_t stride, size_t count, size_t dims, size_t num_subvectors,
+                                       size_t num_centroids, lb200_metric_kind_t metric_kind, size_t max_iter, uint64_t seed,
+                                       uint32_t const* init_rows, float* codebook, lb200_error_t* error) {
+    int rounds = 0;
+    guarded(error, [&] {
+        require_device();
+        if (metric_kind != lb200_metric_l2sq_k && metric_kind != lb200_metric_cos_k)
+            throw CudaError("pq training: l2sq or cos");
+        if (stride % 4)
+            throw CudaError("pq training: stride must be a multiple of 4 bytes");
+        if (num_centroids > 256)
+            throw CudaError("number of centroids must fit in a byte");
+        DeviceTemp dcb(num_centroids * dims * 4);
+        rounds = train_pq_codebook((const float*)d_vectors, stride / 4, count, dims, num_subvectors, num_centroids,
+                                   metric_kind == lb200_metric_cos_k, max_iter, seed, init_rows, dcb.as<float>(), 0);
+        LB_CUDA(cudaMemcpy(codebook, dcb.p, num_centroids * dims * 4, cudaMemcpyDeviceToHost));
+    });
+    return rounds;
+}
+
+LB200_EXPORT int lb200_train_pq(float const* vectors, size_t count, size_t dims, size_t num_subvectors, size_t num_centroids,
+                                lb200_metric_kind_t metric_kind, size_t max_iter, uint64_t seed, uint32_t const* init_rows,
+                                float* codebook, lb200_error_t* error) {
+    int rounds = 0;
+    guarded(error, [&] {
+        require_device();
+        DeviceTemp dv(count * dims * 4);
+        LB_CUDA(cudaMemcpy(dv.p, vectors, count * dims * 4, cudaMemcpyHostToDevice));
+        lb200_error_t e2 = nullptr;
+        rounds = lb200_train_pq_device(dv.p, dims * 4, count, dims, num_subvectors, num_centroids, metric_kind, max_iter, seed,
+                                       init_rows, codebook, &e2);
+        if (e2)
+            throw CudaError(e2);
+    });
+    return rounds;
+}
+
 LB200_EXPORT void lb200_merge_shards_device(lb200_key_t const* d_keys, lb200_distance_t const* d_dists, size_t shards, size_t nq,
                                             size_t count, lb200_key_t* d_out_keys, lb200_distance_t* d_out_dists,
                                             void* cuda_stream, lb200_error_t* error) {

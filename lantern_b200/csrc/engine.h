@@ -191,6 +191,9 @@ void launch_merge_shards(const uint64_t* d_keys, const float* d_dists, size_t sh
                          uint64_t* d_out_keys, float* d_out_dists, cudaStream_t stream);
 // build.cu
 void build_pending(Index& idx);
+// kmeans.cu
+int train_pq_codebook(const float* d_vectors, size_t stride_floats, size_t n, size_t dims, size_t nsub, size_t ncent, bool cosine,
+                      size_t max_iter, uint64_t seed, const uint32_t* init_rows, float* d_codebook, cudaStream_t stream);
 
 int device_sm_count();
 void require_device();

@@ -904,3 +904,57 @@ void ora_exact_search(const void* dataset, size_t n, size_t dataset_stride, cons
     }
     free(top.e);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * PQ codebook training.  Restates lantern_hnsw/src/hnsw/product_quantization.c:51-293 (k distinct dataset rows as
+ * initial centres; assign by usearch_distance with strict '<'; centre = float mean of its members, empty clusters keep
+ * their centre; stop when mean_c distance(old_c, new_c) <= 0.1 or after max_iter rounds; one k-means per subvector).
+ * PARITY UNPINNED against a reference binary: that file needs postgres.h and cannot be compiled here, and its initial
+ * rows come from Postgres' PRNG -- so the initial rows are an INPUT here (init_rows[nsub][ncent]).
+ * ---------------------------------------------------------------------------------------- */
+int ora_kmeans(const float* data, size_t n, size_t dims, size_t nsub, size_t ncent, int metric, size_t max_iter,
+               const uint32_t* init_rows, float* codebook) {
+    size_t sd = dims / nsub, s, c, i, j, it;
+    uint32_t* assign = (uint32_t*)malloc(n * sizeof(uint32_t));
+    float* old = (float*)malloc(ncent * sd * sizeof(float));
+    float* sum = (float*)malloc(sd * sizeof(float));
+    int rounds = 0;
+    for (s = 0; s < nsub; ++s) {
+        for (c = 0; c < ncent; ++c)
+            memcpy(codebook + c * dims + s * sd, data + (size_t)init_rows[s * ncent + c] * dims + s * sd, sd * sizeof(float));
+        for (it = 0; it < max_iter; ++it) {
+            if ((int)(it + 1) > rounds)
+                rounds = (int)(it + 1);
+            for (i = 0; i < n; ++i) {
+                float best = 3.402823466e+38f;
+                uint32_t bc = 0;
+                for (c = 0; c < ncent; ++c) {
+                    float d = ora_distance(data + i * dims + s * sd, codebook + c * dims + s * sd, ORA_F32, sd, metric);
+                    if (d < best)
+                        best = d, bc = (uint32_t)c;
+                }
+                assign[i] = bc;
+            }
+            float shift = 0.f;
+            for (c = 0; c < ncent; ++c) {
+                size_t cnt = 0;
+                memcpy(old + c * sd, codebook + c * dims + s * sd, sd * sizeof(float));
+                memset(sum, 0, sd * sizeof(float));
+                for (i = 0; i < n; ++i)
+                    if (assign[i] == c) {
+                        for (j = 0; j < sd; ++j)
+                            sum[j] += data[i * dims + s * sd + j];
+                        cnt++;
+                    }
+                if (cnt)
+                    for (j = 0; j < sd; ++j)
+                        codebook[c * dims + s * sd + j] = sum[j] / (float)cnt;
+                shift += ora_distance(old + c * sd, codebook + c * dims + s * sd, ORA_F32, sd, metric);
+            }
+            if (shift / (float)ncent <= 0.1f)
+                break;
+        }
+    }
+    free(assign), free(old), free(sum);
+    return rounds;
+}

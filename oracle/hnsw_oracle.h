@@ -74,6 +74,9 @@ void ora_pq_decompress(const float* codebook, size_t dims, size_t num_centroids,
 void ora_exact_search(const void* dataset, size_t n, size_t dataset_stride, const void* queries, size_t nq,
                       size_t queries_stride, int kind, size_t dims, int metric, size_t k, uint64_t* keys,
                       float* distances);
+/* PQ codebook training (product_quantization.c restated; initial rows are an input; parity unpinned, see .c) */
+int ora_kmeans(const float* data, size_t n, size_t dims, size_t nsub, size_t ncent, int metric, size_t max_iter,
+               const uint32_t* init_rows, float* codebook);
 /* level generator alone, for tests: returns the i-th (0-based) level of a fresh generator */
 int ora_level_sequence(size_t connectivity, size_t count, int16_t* out);
 

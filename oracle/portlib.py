@@ -69,6 +69,8 @@ def lib():
         L.ora_exact_search.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int,
                                        C.c_size_t, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
         L.ora_level_sequence.argtypes = [C.c_size_t, C.c_size_t, C.c_void_p]
+        L.ora_kmeans.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_void_p,
+                                 C.c_void_p]
         _lib = L
     return _lib
 
@@ -218,3 +220,12 @@ def level_sequence(M, count):
     out = np.zeros(count, np.int16)
     lib().ora_level_sequence(M, count, out.ctypes.data)
     return out
+
+
+def kmeans(data, num_subvectors, num_centroids, init_rows, metric="l2sq", max_iter=20):
+    data = np.ascontiguousarray(data, dtype=np.float32)
+    init_rows = np.ascontiguousarray(init_rows, dtype=np.uint32)
+    cb = np.zeros((num_centroids, data.shape[1]), np.float32)
+    rounds = lib().ora_kmeans(data.ctypes.data, len(data), data.shape[1], num_subvectors, num_centroids, METRIC[metric], max_iter,
+                              init_rows.ctypes.data, cb.ctypes.data)
+    return cb, rounds

@@ -82,3 +82,26 @@ def test_pq_batched_build_recall(eng, port):
     rec = np.mean([len(set(a.tolist()) & set((b + 1).tolist())) / 10 for a, b in zip(gk, tk)])
     assert rec > 0.85, rec  # hnsw_pq_index.sql:129-131: index recall within 0.1 of PQ-exact
     assert np.allclose(np.sort(gd[:, 0]), np.sort(np.minimum(gd[:, 0], td[:, 0])), rtol=1e-4) or rec > 0.9
+
+
+@pytest.mark.parametrize("metric", ["l2sq", "cos"])
+def test_codebook_training_matches_oracle(eng, port, metric):
+    """GPU k-means (product_quantization.c semantics) against the CPU restatement from the same initial rows."""
+    rng = np.random.default_rng(6)
+    n, d, nsub, ncent = 4000, 24, 4, 16
+    centers = rng.standard_normal((ncent, d)).astype(np.float32) * 3
+    X = (centers[rng.integers(0, ncent, n)] + rng.standard_normal((n, d))).astype(np.float32)
+    init = np.stack([rng.choice(n, ncent, replace=False) for _ in range(nsub)]).astype(np.uint32)
+    gcb, grounds = eng.train_pq(X, nsub, ncent, metric, max_iter=25, init_rows=init)
+    pcb, prounds = port.kmeans(X, nsub, ncent, init, metric, max_iter=25)
+    assert grounds == prounds
+    assert np.allclose(gcb, pcb, rtol=1e-4, atol=1e-4)
+    # and the trained codebook is usable end to end
+    g = eng.Index(d, metric, "f32", M=8, efc=48, ef=32, pq=True, num_centroids=ncent, num_subvectors=nsub, codebook=gcb)
+    g.reserve(n)
+    g.add_batch(np.arange(1, n + 1, dtype=np.uint64), X)
+    k, dd, _ = g.search_batch(X[:50], 5)
+    assert (k[:, 0] > 0).all()
+    # random initialisation path (no init rows): distinct rows, converges
+    cb2, r2 = eng.train_pq(X, nsub, ncent, metric, max_iter=25, seed=7)
+    assert r2 >= 1 and np.isfinite(cb2).all()
