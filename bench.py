@@ -627,7 +627,7 @@ def run_ours(args, wl):
                        "l2_policy": "inputs larger than L2: %.1f GB corpus gathered at random; %d distinct query batches cycled" % ((hi - lo) * rowb / 1e9, pool),
                        "generator": ("64 random prototypes XOR 10%% bit flips, seeds %d/%d/%d" % (SEED_P, SEED_CORPUS, SEED_QUERY)) if kind == "b1" else
                        "x = z P + %.2f eps, z~N(0,I_%d), seeds %d/%d/%d" % (NOISE, LATENT, SEED_P, SEED_CORPUS, SEED_QUERY)},
-            "recall_at_10": rec, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "recall_at_10": rec if k == 10 else None, "recall_at_k": rec, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "parity": parity, "sharding": shard_info, "pq": pq_info,
             "build": {"vectors_per_s": (hi - lo) / t_build, "seconds": t_build, "datagen_seconds": t_gen},
         }

@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <unordered_set>
@@ -236,12 +237,13 @@ LB200_EXPORT size_t lb200_search_ef(lb200_index_t h, void const* query, lb200_sc
         // (already returned + count) neighbours of the same query, of which the new tail is handed out: the caller sees
         // the same contract -- never a result twice, ascending distance -- and, unlike the reference,
         // never loses reachable results.
-        size_t skip = 0;
         if (continue_search) {
             if (idx->stream_query_.size() != qbytes || memcmp(idx->stream_query_.data(), query, qbytes) != 0)
                 throw CudaError("continue_search: no preceding search of this query on this index");
-            skip = idx->stream_consumed_;
+        } else {
+            idx->stream_returned_.clear();
         }
+        const size_t skip = idx->stream_returned_.size();
         const size_t want = skip + count;
         if (want > 4096)
             throw CudaError("continue_search: more than 4096 results requested in total");
@@ -249,12 +251,18 @@ LB200_EXPORT size_t lb200_search_ef(lb200_index_t h, void const* query, lb200_sc
         std::vector<float> d(want);
         size_t c = 0;
         idx->search_host(query, 1, qbytes, kind, want, ef, k.data(), d.data(), &c);
-        found = c > skip ? c - skip : 0;
-        // dump_to writes only `found` entries (index.hpp:2426-2433)
-        memcpy(keys, k.data() + skip, found * sizeof(uint64_t));
-        memcpy(distances, d.data() + skip, found * sizeof(float));
+        // hand out the closest `count` results that were not returned before (a wider beam may rank old results
+        // differently, so filtering is by key, not by position); dump_to writes only `found` entries (index.hpp:2426-2433)
+        std::vector<uint64_t> seen(idx->stream_returned_);
+        std::sort(seen.begin(), seen.end());
+        for (size_t i = 0; i < c && found < count; ++i) {
+            if (std::binary_search(seen.begin(), seen.end(), k[i]))
+                continue;
+            keys[found] = k[i], distances[found] = d[i];
+            idx->stream_returned_.push_back(k[i]);
+            ++found;
+        }
         idx->stream_query_.assign((const uint8_t*)query, (const uint8_t*)query + qbytes);
-        idx->stream_consumed_ = skip + found;
     });
     return found;
 }

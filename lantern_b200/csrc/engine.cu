@@ -87,8 +87,6 @@ Index::~Index() {
     cudaFree(d_codebook_), cudaFree(scratch_.visited), cudaFree(scratch_.touched), cudaFree(scratch_.counters);
     cudaFree(d_query_buf_), cudaFree(d_io_buf_);
     cudaFree(d_pq_pair_), cudaFree(d_pq_norm_), cudaFree(d_pending_raw_);
-    if (h_pinned_)
-        cudaFreeHost(h_pinned_);
     if (ev0_)
         cudaEventDestroy(ev0_);
     if (ev1_)
@@ -143,24 +141,10 @@ uint8_t* Index::query_buffer(size_t bytes) {
     return d_query_buf_;
 }
 
-void* Index::pinned(size_t bytes) {
-    if (bytes > pinned_bytes_) {
-        if (h_pinned_)
-            LB_CUDA(cudaFreeHost(h_pinned_));
-        h_pinned_ = nullptr;
-        pinned_bytes_ = round_up(bytes + bytes / 4, 4096);
-        LB_CUDA(cudaMallocHost(&h_pinned_, pinned_bytes_));
-    }
-    return h_pinned_;
-}
-
 // ---- staging of new vectors (usearch_add: U/c/lib.cpp:357-365 -> index_dense.hpp:1395-1426) ---------
 static void check_input_kind(const IndexConfig& cfg, int kind) {
-    if (kind == SK_F32) {
-        if (cfg.metric_kind == MK_HAMMING && cfg.scalar_kind == SK_B1)
-            return; // f32 -> sign bits is what cast_gt does; allowed
-        return;
-    }
+    if (kind == SK_F32)
+        return; // cast to the storage kind on the device (f32 -> sign bits for b1 is what cast_gt does)
     if (kind == SK_B1 && cfg.scalar_kind == SK_B1)
         return;
     throw CudaError("vectors must be passed as f32, or as packed bits (b1) for a b1 index");

@@ -136,24 +136,19 @@ class Index {
 
     // search scratch
     SearchScratch scratch_{};
-    size_t scratch_capacity_ = 0;
     uint8_t* d_query_buf_ = nullptr;
     size_t query_buf_bytes_ = 0;
     void* d_io_buf_ = nullptr;
     size_t io_buf_bytes_ = 0;
-    void* h_pinned_ = nullptr;
-    size_t pinned_bytes_ = 0;
-    SearchStats last_stats_{};
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     uint32_t last_nq_ = 0;
     std::mutex mu_;
     // streaming state of the single-query entry point (usearch_search_ef continue_search, scan.c:240-292)
     std::vector<uint8_t> stream_query_;
-    size_t stream_consumed_ = 0;
+    std::vector<uint64_t> stream_returned_; // keys handed out so far for stream_query_
 
     void ensure_scratch(uint32_t ctas);
     void* io_buffer(size_t bytes);
-    void* pinned(size_t bytes);
     uint8_t* query_buffer(size_t bytes);
 };
 

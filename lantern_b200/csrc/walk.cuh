@@ -44,12 +44,14 @@ struct WalkSmem {
     uint32_t* top_i;
     uint32_t* cand_id;
     float* cand_d;
+    uint32_t* limbo; // unexpanded entries evicted from the top list at exactly the current radius (distance ties)
     WalkCtrl* ctrl;
 };
 
 struct WalkLayout {
-    size_t full, top_d, top_i, cand_id, cand_d, ctrl, total;
+    size_t full, top_d, top_i, cand_id, cand_d, limbo, ctrl, total;
 };
+constexpr uint32_t kLimboCap = 64;
 
 // `stage_bytes` of value/row staging, `nbar` mbarriers, a top list of `top_cap` entries, candidate arrays of `cand_cap`.
 __host__ __device__ inline WalkLayout walk_layout_bytes(size_t stage_bytes, uint32_t nbar, uint32_t top_cap, uint32_t cand_cap) {
@@ -61,6 +63,7 @@ __host__ __device__ inline WalkLayout walk_layout_bytes(size_t stage_bytes, uint
     l.top_i = o, o += (size_t)top_cap * 4;
     l.cand_id = o, o += (size_t)cand_cap * 4;
     l.cand_d = o, o += (size_t)cand_cap * 4;
+    l.limbo = o, o += (size_t)kLimboCap * 4;
     o = (o + 15) & ~(size_t)15;
     l.ctrl = o, o += sizeof(WalkCtrl);
     l.total = o;
@@ -99,8 +102,13 @@ inline int pick_nq(uint32_t row_bytes) {
 // Warp-cooperative sorted insert == sorted_buffer_gt::insert (index.hpp:752-763): position = lower_bound
 // (new element goes BEFORE equal ones), tail evicted when the list is full.
 // Precondition (index.hpp:3470): size < L || d < top_d[size-1].
+// `ev_d`/`ev_i` receive the evicted tail (ev_i = kNoNeighbor when nothing was evicted).
 __device__ __forceinline__ void top_insert(float* td, uint32_t* ti, uint32_t& size, uint32_t& cursor, uint32_t L, float d,
-                                           uint32_t id, int lane) {
+                                           uint32_t id, int lane, float& ev_d, uint32_t& ev_i) {
+    ev_i = kNoNeighbor, ev_d = 0.f;
+    if (size == L)
+        ev_d = td[L - 1], ev_i = ti[L - 1];
+    __syncwarp();
     uint32_t pos = 0;
     for (uint32_t b = 0; b < size; b += 32) {
         uint32_t e = b + lane;
@@ -127,6 +135,12 @@ __device__ __forceinline__ void top_insert(float* td, uint32_t* ti, uint32_t& si
     if (pos <= cursor)
         cursor = pos;
 }
+__device__ __forceinline__ void top_insert(float* td, uint32_t* ti, uint32_t& size, uint32_t& cursor, uint32_t L, float d,
+                                           uint32_t id, int lane) {
+    float ev_d;
+    uint32_t ev_i;
+    top_insert(td, ti, size, cursor, L, d, id, lane, ev_d, ev_i);
+}
 
 // state shared by every evaluator / walker
 struct WalkBase {
@@ -147,6 +161,7 @@ struct WalkBase {
         sm.top_i = reinterpret_cast<uint32_t*>(smem_raw + lay.top_i);
         sm.cand_id = reinterpret_cast<uint32_t*>(smem_raw + lay.cand_id);
         sm.cand_d = reinterpret_cast<float*>(smem_raw + lay.cand_d);
+        sm.limbo = reinterpret_cast<uint32_t*>(smem_raw + lay.limbo);
         sm.ctrl = reinterpret_cast<WalkCtrl*>(smem_raw + lay.ctrl);
         warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         st_dist = st_pops = st_hops = 0;
@@ -429,6 +444,11 @@ template <class E> struct WalkerT : E {
     // returns its size (uniform across the CTA).  Visited bits are cleared before returning.
     __device__ __forceinline__ uint32_t beam(int level, uint32_t start, float start_d, uint32_t L, uint32_t skip) {
         uint32_t size = 0, cursor = 0, ntouched = 0; // warp-0 uniform
+        // Distance ties at the eviction boundary: the reference's queue keeps an element after `top` evicted it, and still
+        // expands it while its distance EQUALS the radius (the stop test index.hpp:3445 is a strict '>').  Such elements
+        // wait in `limbo`; they all share one distance (the radius at the time) and die as soon as the radius shrinks.
+        uint32_t limbo_n = 0;
+        float limbo_d = 0.f;
         __syncthreads();
         if (warp == 0) {
             if (lane == 0) {
@@ -443,16 +463,21 @@ template <class E> struct WalkerT : E {
         for (;;) {
             __syncthreads(); // (A) insertions of the previous round are complete
             if (warp == 0) {
-                if (cursor >= size) {
+                if (cursor >= size && limbo_n == 0) {
                     if (lane == 0)
                         sm.ctrl->n = kDone;
                 } else {
-                    const uint32_t c = sm.top_i[cursor];
-                    __syncwarp();
-                    if (lane == 0)
-                        sm.top_i[cursor] = c | kExpandedBit;
-                    __syncwarp();
-                    { // advance the cursor to the next unexpanded entry
+                    uint32_t c;
+                    if (cursor < size) {
+                        c = sm.top_i[cursor];
+                        __syncwarp();
+                        if (lane == 0)
+                            sm.top_i[cursor] = c | kExpandedBit;
+                        __syncwarp();
+                    } else {
+                        c = sm.limbo[--limbo_n]; // distance == radius: not beyond it, so the reference expands it too
+                    }
+                    if (cursor < size) { // advance the cursor to the next unexpanded entry
                         uint32_t nxt = size;
                         for (uint32_t b = cursor + 1; b < size; b += 32) {
                             uint32_t e = b + lane;
@@ -522,9 +547,20 @@ template <class E> struct WalkerT : E {
                         const float d = __shfl_sync(0xffffffffu, dj, b);
                         if (size < L || d < sm.top_d[size - 1]) {
                             const uint32_t id = sm.cand_id[base + b];
-                            top_insert(sm.top_d, sm.top_i, size, cursor, L, d, id, lane);
+                            float ev_d;
+                            uint32_t ev_i;
+                            top_insert(sm.top_d, sm.top_i, size, cursor, L, d, id, lane, ev_d, ev_i);
                             if (level == 0 && (g.flags & 2u) && lane == 0)
                                 prefetch_l2(g.adj0 + (size_t)id * g.M0);
+                            const float radius = sm.top_d[size - 1];
+                            if (limbo_n && radius < limbo_d)
+                                limbo_n = 0; // the radius shrank below the waiting ties: they can never be expanded
+                            if (ev_i != kNoNeighbor && !(ev_i & kExpandedBit) && ev_d == radius && limbo_n < kLimboCap) {
+                                if (lane == 0)
+                                    sm.limbo[limbo_n] = ev_i;
+                                limbo_n++, limbo_d = radius;
+                                __syncwarp();
+                            }
                         }
                     }
                 }

