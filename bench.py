@@ -48,6 +48,8 @@ WORKLOADS = {
     "cfg4s": dict(n=1_000_000, dim=1536, metric="l2sq", M=16, efc=128, ef=64, batch=4096, k=100, pq=(96, 256),
                   desc="cfg4s (1/10 scale): 1M x d1536 f32 -> PQ 96x256, l2sq, M=16 efc=128 ef=64 (expansion 100), batch-4096 k=100"),
     # BASELINE configs[4] is 50M x 768-byte binary vectors over 8 GPUs: one shard's worth (6.25M) on one GPU
+    "cfg5": dict(n=50_000_000, dim=6144, kind="b1", metric="hamming", M=16, efc=128, ef=64, batch=4096, k=10,
+                 desc="cfg5: 50M x 6144-bit (768 B) hamming, M=16 efc=128 ef=64, batch-4096 k=10 (build + search, 8 GPUs)"),
     "cfg5s": dict(n=6_250_000, dim=6144, kind="b1", metric="hamming", M=16, efc=128, ef=64, batch=4096, k=10,
                   desc="cfg5s (one of 8 shards of cfg5): 6.25M x 6144-bit (768 B) hamming, M=16 efc=128 ef=64, batch-4096 k=10"),
     "cfg5t": dict(n=500_000, dim=6144, kind="b1", metric="hamming", M=16, efc=128, ef=64, batch=4096, k=10,
@@ -383,33 +385,39 @@ def run_ours(args, wl):
     #      the unsharded single-GPU graph at the workload's ef (measured here on rank 0), and report both. ----
     shard_info = None
     if world > 1:
-        # every rank also builds the FULL graph (it fits in HBM): rank 0 takes the unsharded recall target from it, and all
-        # ranks use it for the clearly-labelled "replicated" comparison below
+        # recall target = recall of the UNSHARDED graph at the workload's ef.  Small corpora: every rank builds the full
+        # graph (rank 0 takes the target from it; all ranks use it for the labelled "replicated" comparison below).
+        # Large corpora: pass the 1-GPU bench's recall with --recall-target instead of rebuilding 10M+ rows per rank.
         target = torch.zeros(1, dtype=torch.float64, device=dev)
-        Xfull = gen_t(n, dim, SEED_CORPUS, dev)
-        full = api.Index(dim, wl["metric"], kind, M=wl["M"], efc=wl["efc"], ef=ef)
-        full.reserve(n)
-        full.add_batch_device(np.arange(1, n + 1, dtype=np.uint64), Xfull.data_ptr(), n, rowb, kind)
-        full.build()
-        del Xfull
-        fk = torch.empty((B, k), dtype=torch.int64, device=dev)
-        fd = torch.empty((B, k), dtype=torch.float32, device=dev)
-        full.search_batch_device(Q.data_ptr(), B, rowb, kind, k, ef, fk.data_ptr(), fd.data_ptr(), 0, stream.cuda_stream)
-        torch.cuda.synchronize()
-        if rank == 0:
-            target[0] = recall_at_k(fk[:nrec].cpu().numpy(), truth)
+        full = None
+        build_full = args.recall_target <= 0 and args.shard_ef >= 0 or args.replicated_comparison
+        if build_full and n * rowb <= 8e9:
+            Xfull = gen_t(n, dim, SEED_CORPUS, dev)
+            full = api.Index(dim, wl["metric"], kind, M=wl["M"], efc=wl["efc"], ef=ef)
+            full.reserve(n)
+            full.add_batch_device(np.arange(1, n + 1, dtype=np.uint64), Xfull.data_ptr(), n, rowb, kind)
+            full.build()
+            del Xfull
+            fk = torch.empty((B, k), dtype=torch.int64, device=dev)
+            fd = torch.empty((B, k), dtype=torch.float32, device=dev)
+            full.search_batch_device(Q.data_ptr(), B, rowb, kind, k, ef, fk.data_ptr(), fd.data_ptr(), 0, stream.cuda_stream)
+            torch.cuda.synchronize()
+            if rank == 0:
+                target[0] = recall_at_k(fk[:nrec].cpu().numpy(), truth)
+        if args.recall_target > 0:
+            target[0] = args.recall_target
         dist.broadcast(target, 0)
         target = float(target.item())
         sweep = {}
         cands = sorted(set([e for e in (k, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48, 52, 56, 64, 72, 80, 96, 112, 128) if k <= e <= ef] + [ef]))
         chosen = ef
-        for e in cands:
+        for e in (cands if args.shard_ef == 0 else []):
             state["ef"] = e
             res = step_device(0)
             torch.cuda.synchronize()
             r = recall_at_k(res[:nrec].cpu().numpy(), truth)
             sweep[e] = r
-            if r >= target:
+            if r >= target and target > 0:
                 chosen = e
                 break
         if args.shard_ef > 0:
@@ -419,29 +427,42 @@ def run_ours(args, wl):
         state["ef"] = chosen
         ef_shard = chosen
         shard_info = {"recall_target_unsharded_1gpu": target, "sweep_merged_recall_by_ef": sweep, "ef_per_shard": chosen}
-        # replicated comparison (NOT the headline): every GPU holds the whole graph and serves its own B-query batches,
-        # no exchange step; weak scaling in queries.  Same kernel, same ef as 1 GPU, same recall as 1 GPU.
+        def timed(fn, reps):
+            for s_ in range(3):
+                fn(s_)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for s_ in range(reps):
+                fn(s_)
+            e1.record(stream)
+            barrier()
+            tr = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+            return float(tr.item()) / 1e3
+
         reps = max(10, min(args.steps, 100))
-        for s in range(3):
-            full.search_batch_device(Q[((s + rank) % pool) * B].data_ptr(), B, rowb, kind, k, ef, fk.data_ptr(), fd.data_ptr(), 0,
-                                     stream.cuda_stream)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for s in range(reps):
-            full.search_batch_device(Q[((s + rank) % pool) * B].data_ptr(), B, rowb, kind, k, ef, fk.data_ptr(), fd.data_ptr(), 0,
-                                     stream.cuda_stream)
-        e1.record(stream)
-        barrier()
-        tr = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
-        shard_info["replicated_comparison"] = {
-            "value": world * reps * B / (float(tr.item()) / 1e3), "unit": "queries/s", "scaling": "weak",
-            "what": "NOT the headline: full corpus replicated on every GPU, each GPU serves its own %d-query batches at ef=%d, "
-                    "no collective; recall = the 1-GPU recall" % (B, ef)}
-        full.close()
-        del full
-        torch.cuda.empty_cache()
+        if chosen != ef:  # (i) of SURVEY 8e: same ef on every shard (higher recall, little speed-up)
+            state["ef"] = ef
+            res = step_device(0)
+            torch.cuda.synchronize()
+            r_same = recall_at_k(res[:nrec].cpu().numpy(), truth)
+            shard_info["same_ef"] = {"ef_per_shard": ef, "value": reps * B / timed(step_device, reps), "unit": "queries/s",
+                                     "merged_recall": r_same}
+            state["ef"] = chosen
+        if full is not None:
+            # replicated comparison (NOT the headline): every GPU holds the whole graph and serves its own B-query batches,
+            # no exchange step; weak scaling in queries.  Same kernel, same ef as 1 GPU, same recall as 1 GPU.
+            def rep_step(s_):
+                full.search_batch_device(Q[((s_ + rank) % pool) * B].data_ptr(), B, rowb, kind, k, ef, fk.data_ptr(), fd.data_ptr(), 0,
+                                         stream.cuda_stream)
+            shard_info["replicated_comparison"] = {
+                "value": world * reps * B / timed(rep_step, reps), "unit": "queries/s", "scaling": "weak",
+                "what": "NOT the headline: full corpus replicated on every GPU, each GPU serves its own %d-query batches at ef=%d, "
+                        "no collective; recall = the 1-GPU recall" % (B, ef)}
+            full.close()
+            del full
+            torch.cuda.empty_cache()
 
     # ---- warm-up, then K timed steps on the device ----
     for s in range(args.warmup):
@@ -647,6 +668,9 @@ def main():
     ap.add_argument("--shard-ef", type=int, default=0,
                     help="--gpus > 1: per-shard ef; 0 = recall-matched (smallest ef_s whose merged recall reaches the unsharded "
                          "1-GPU recall at the workload's ef), -1 = same ef as the workload")
+    ap.add_argument("--recall-target", type=float, default=0.0,
+                    help="--gpus > 1: unsharded 1-GPU recall to match (0 = measure it here by building the full graph)")
+    ap.add_argument("--replicated-comparison", action="store_true", help="--gpus > 1: force the replicated comparison")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="bound on the cpu_baseline search time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pq-ref-rows", type=int, default=100_000, help="pq workloads: rows the reference indexes for cpu_baseline")
