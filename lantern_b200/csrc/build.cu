@@ -53,11 +53,11 @@ struct BuildLaunch {
 };
 
 template <class W>
-__global__ void __launch_bounds__(kWalkThreads) build_insert_kernel(const BuildLaunch p, const uint32_t R) {
+__global__ void __launch_bounds__(kWalkThreads) build_insert_kernel(const __grid_constant__ BuildLaunch p, const uint32_t R) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const WalkLayout lay = W::layout(p.g, R, p.top_cap, p.g.M0 + 1);
-    W w;
-    w.init(p.g, smem_raw, lay, R, p.s);
+    W w(p.g);
+    w.init(smem_raw, lay, R, p.s);
     WalkSmem& sm = w.sm;
     const uint32_t M = p.g.M, M0 = p.g.M0;
 
@@ -97,9 +97,9 @@ __global__ void __launch_bounds__(kWalkThreads) build_insert_kernel(const BuildL
         }
     }
     if (threadIdx.x == 0) {
-        atomicAdd(&p.s.counters[1], w.st_dist);
-        atomicAdd(&p.s.counters[2], w.st_pops);
-        atomicAdd(&p.s.counters[3], w.st_hops);
+        atomicAdd(&p.s.counters[1], (unsigned long long)w.st_dist);
+        atomicAdd(&p.s.counters[2], (unsigned long long)w.st_pops);
+        atomicAdd(&p.s.counters[3], (unsigned long long)w.st_hops);
     }
 }
 
@@ -116,12 +116,12 @@ __global__ void segment_heads_kernel(const unsigned long long* __restrict__ keys
 }
 
 template <class W>
-__global__ void __launch_bounds__(kWalkThreads) build_reverse_kernel(const BuildLaunch p, const uint32_t R) {
+__global__ void __launch_bounds__(kWalkThreads) build_reverse_kernel(const __grid_constant__ BuildLaunch p, const uint32_t R) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t M = p.g.M, M0 = p.g.M0;
     const WalkLayout lay = W::layout(p.g, R, M0 + 2, M0 + 1);
-    W w;
-    w.init(p.g, smem_raw, lay, R, p.s);
+    W w(p.g);
+    w.init(smem_raw, lay, R, p.s);
     WalkSmem& sm = w.sm;
     uint32_t* lst_i = reinterpret_cast<uint32_t*>(smem_raw + lay.total);
     float* lst_d = reinterpret_cast<float*>(lst_i + M0);
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kWalkThreads) build_reverse_kernel(const Build
             list[j] = j < cnt ? lst_i[j] : kNoNeighbor;
     }
     if (threadIdx.x == 0)
-        atomicAdd(&p.s.counters[1], w.st_dist);
+        atomicAdd(&p.s.counters[1], (unsigned long long)w.st_dist);
 }
 
 // reference level generator (index.hpp:3208-3212 with libstdc++'s minstd_rand0 / generate_canonical<double,53>)

@@ -54,7 +54,7 @@ struct GraphView {
     const float* codebook; // [num_centroids][dims]
     const float* pq_pair;  // [nsub][ncent][ncent] centroid-pair table (l2sq: |ca-cb|^2 ; cos: ca.cb)
     const float* pq_norm;  // [nsub][ncent] |centroid slice|^2 (cos)
-    uint32_t flags;        // tuning: 1 = prefetch adjacency of every measured node, 2 = of accepted nodes only, 4 = evict-first rows
+    uint32_t flags;        // tuning: 1 = L2-prefetch the adjacency of every measured node, 2 = of accepted nodes only
     uint32_t dims, num_centroids, num_subvectors;
 };
 

@@ -27,11 +27,11 @@ namespace lb200 {
 namespace {
 
 template <class W>
-__global__ void __launch_bounds__(kWalkThreads) hnsw_search_kernel(const SearchLaunch p, const uint32_t R) {
+__global__ void __launch_bounds__(kWalkThreads) hnsw_search_kernel(const __grid_constant__ SearchLaunch p, const uint32_t R) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const WalkLayout lay = W::layout(p.g, R, p.L, p.g.M0);
-    W w;
-    w.init(p.g, smem_raw, lay, R, p.s);
+    W w(p.g);
+    w.init(smem_raw, lay, R, p.s);
     WalkSmem& sm = w.sm;
 
     for (;;) {
@@ -67,9 +67,9 @@ __global__ void __launch_bounds__(kWalkThreads) hnsw_search_kernel(const SearchL
         }
     }
     if (threadIdx.x == 0) {
-        atomicAdd(&p.s.counters[1], w.st_dist);
-        atomicAdd(&p.s.counters[2], w.st_pops);
-        atomicAdd(&p.s.counters[3], w.st_hops);
+        atomicAdd(&p.s.counters[1], (unsigned long long)w.st_dist);
+        atomicAdd(&p.s.counters[2], (unsigned long long)w.st_pops);
+        atomicAdd(&p.s.counters[3], (unsigned long long)w.st_hops);
     }
 }
 

@@ -142,19 +142,156 @@ __device__ __forceinline__ void top_insert(float* td, uint32_t* ti, uint32_t& si
     top_insert(td, ti, size, cursor, L, d, id, lane, ev_d, ev_i);
 }
 
+// ---- the top-`L` list of one walk (warp 0 only).  Two stores with identical semantics ---------------------------
+// sorted_buffer_gt (index.hpp:668-780): ascending by distance, insert at lower_bound (before equal elements), evict the
+// tail when full; entries carry an "expanded" flag (kExpandedBit) that replaces the reference's separate candidate heap.
+struct TopSmem { // any L: arrays in shared memory
+    float* td;
+    uint32_t* ti;
+    uint32_t size, cursor, L;
+    __device__ __forceinline__ void init(const WalkSmem& sm, uint32_t cap, float d, uint32_t id, int lane) {
+        td = sm.top_d, ti = sm.top_i, L = cap, size = 1, cursor = 0;
+        if (lane == 0)
+            td[0] = d, ti[0] = id;
+        __syncwarp();
+    }
+    // closest unexpanded entry -> c (marked expanded); false when none is left
+    __device__ __forceinline__ bool pop(uint32_t& c, int lane) {
+        if (cursor >= size)
+            return false;
+        c = ti[cursor];
+        __syncwarp();
+        if (lane == 0)
+            ti[cursor] = c | kExpandedBit;
+        __syncwarp();
+        uint32_t nxt = size;
+        for (uint32_t b = cursor + 1; b < size; b += 32) {
+            uint32_t e = b + lane;
+            bool un = e < size && !(ti[e] & kExpandedBit);
+            uint32_t m = __ballot_sync(0xffffffffu, un);
+            if (m) {
+                nxt = b + __ffs(m) - 1;
+                break;
+            }
+        }
+        cursor = nxt;
+        return true;
+    }
+    __device__ __forceinline__ float radius(int) const { return td[size - 1]; }
+    __device__ __forceinline__ void insert(float d, uint32_t id, int lane, float& ev_d, uint32_t& ev_i) {
+        top_insert(td, ti, size, cursor, L, d, id, lane, ev_d, ev_i);
+    }
+    __device__ __forceinline__ void flush(int) {}
+};
+
+struct TopRegs { // L <= 64: element e lives in lane e & 31, register e >> 5 of warp 0
+    static constexpr int kRegs = 2;
+    static constexpr uint32_t kCap = 32 * kRegs;
+    float rd[kRegs];
+    uint32_t ri[kRegs];
+    float* td;
+    uint32_t* ti;
+    uint32_t size, L;
+    __device__ __forceinline__ void init(const WalkSmem& sm, uint32_t cap, float d, uint32_t id, int lane) {
+        td = sm.top_d, ti = sm.top_i, L = cap, size = 1;
+#pragma unroll
+        for (int r = 0; r < kRegs; ++r)
+            rd[r] = INFINITY, ri[r] = kNoNeighbor;
+        if (lane == 0)
+            rd[0] = d, ri[0] = id;
+    }
+    __device__ __forceinline__ bool pop(uint32_t& c, int lane) {
+        bool got = false;
+#pragma unroll
+        for (int r = 0; r < kRegs; ++r) {
+            if (!got && (uint32_t)(r * 32) < size) {
+                const bool un = (uint32_t)(r * 32 + lane) < size && !(ri[r] & kExpandedBit);
+                const uint32_t m = __ballot_sync(0xffffffffu, un);
+                if (m) {
+                    const int l = __ffs(m) - 1;
+                    c = __shfl_sync(0xffffffffu, ri[r], l);
+                    if (lane == l)
+                        ri[r] |= kExpandedBit;
+                    got = true;
+                }
+            }
+        }
+        return got;
+    }
+    __device__ __forceinline__ float get_d(uint32_t e) const {
+        float v = 0.f;
+#pragma unroll
+        for (int r = 0; r < kRegs; ++r)
+            if ((e >> 5) == (uint32_t)r)
+                v = __shfl_sync(0xffffffffu, rd[r], e & 31);
+        return v;
+    }
+    __device__ __forceinline__ uint32_t get_i(uint32_t e) const {
+        uint32_t v = 0;
+#pragma unroll
+        for (int r = 0; r < kRegs; ++r)
+            if ((e >> 5) == (uint32_t)r)
+                v = __shfl_sync(0xffffffffu, ri[r], e & 31);
+        return v;
+    }
+    __device__ __forceinline__ float radius(int) const { return get_d(size - 1); }
+    __device__ __forceinline__ void insert(float d, uint32_t id, int lane, float& ev_d, uint32_t& ev_i) {
+        ev_i = kNoNeighbor, ev_d = 0.f;
+        if (size == L)
+            ev_d = get_d(L - 1), ev_i = get_i(L - 1);
+        uint32_t pos = 0; // lower_bound: entries strictly below d form a prefix
+#pragma unroll
+        for (int r = 0; r < kRegs; ++r)
+            if ((uint32_t)(r * 32) < size)
+                pos += __popc(__ballot_sync(0xffffffffu, (uint32_t)(r * 32 + lane) < size && rd[r] < d));
+        const uint32_t last = (size == L) ? L - 1 : size;
+        float pd[kRegs];
+        uint32_t pi[kRegs];
+#pragma unroll
+        for (int r = 0; r < kRegs; ++r) { // value of element e-1 as seen by the holder of element e
+            pd[r] = __shfl_up_sync(0xffffffffu, rd[r], 1);
+            pi[r] = __shfl_up_sync(0xffffffffu, ri[r], 1);
+            if (r > 0) {
+                const float cd = __shfl_sync(0xffffffffu, rd[r - 1], 31);
+                const uint32_t ci = __shfl_sync(0xffffffffu, ri[r - 1], 31);
+                if (lane == 0)
+                    pd[r] = cd, pi[r] = ci;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kRegs; ++r) {
+            const uint32_t e = r * 32 + lane;
+            if (e > pos && e <= last)
+                rd[r] = pd[r], ri[r] = pi[r];
+            else if (e == pos)
+                rd[r] = d, ri[r] = id;
+        }
+        size = last + 1;
+    }
+    __device__ __forceinline__ void flush(int lane) {
+#pragma unroll
+        for (int r = 0; r < kRegs; ++r) {
+            const uint32_t e = r * 32 + lane;
+            if (e < size)
+                td[e] = rd[r], ti[e] = ri[r];
+        }
+        __syncwarp();
+    }
+};
+
 // state shared by every evaluator / walker
 struct WalkBase {
-    GraphView g;
+    const GraphView& g; // the kernel's own (__grid_constant__) parameter: fields are read from the constant bank
     WalkSmem sm;
     uint32_t* vis;
     uint32_t* touched;
     uint32_t touched_cap;
     size_t words_per_cta;
     int warp, lane;
-    unsigned long long st_dist, st_pops, st_hops; // thread 0's copy is the one that is reported
+    uint32_t st_dist, st_pops, st_hops; // per-launch work counters; thread 0's copy is the one that is reported
 
-    __device__ __forceinline__ void init_base(const GraphView& gv, uint8_t* smem_raw, const WalkLayout& lay, const SearchScratch& s) {
-        g = gv;
+    __device__ __forceinline__ explicit WalkBase(const GraphView& gv) : g(gv) {}
+    __device__ __forceinline__ void init_base(uint8_t* smem_raw, const WalkLayout& lay, const SearchScratch& s) {
         sm.ring = smem_raw;
         sm.full = reinterpret_cast<uint64_t*>(smem_raw + lay.full);
         sm.top_d = reinterpret_cast<float*>(smem_raw + lay.top_d);
@@ -180,16 +317,14 @@ template <int DM, int SK, int NQ> struct RowEval : WalkBase {
     uint4 qreg[NQ];
     float a2;
     uint32_t phase_bits;
-    uint64_t pol;
     uint32_t nchunks, R, SPW;
 
-    __device__ __forceinline__ void init(const GraphView& gv, uint8_t* smem_raw, const WalkLayout& lay, uint32_t ring_slots,
-                                         const SearchScratch& s) {
-        init_base(gv, smem_raw, lay, s);
+    __device__ __forceinline__ explicit RowEval(const GraphView& gv) : WalkBase(gv) {}
+    __device__ __forceinline__ void init(uint8_t* smem_raw, const WalkLayout& lay, uint32_t ring_slots, const SearchScratch& s) {
+        init_base(smem_raw, lay, s);
         nchunks = g.row_bytes / 16;
         R = ring_slots, SPW = ring_slots / kWalkWarps;
         phase_bits = 0;
-        pol = policy_evict_first();
         a2 = 0.f;
         if (threadIdx.x == 0) {
             for (uint32_t i = 0; i < R; ++i)
@@ -218,10 +353,7 @@ template <int DM, int SK, int NQ> struct RowEval : WalkBase {
     __device__ __forceinline__ void issue(uint32_t slot, uint32_t id) {
         uint64_t* bar = &sm.full[slot];
         mbar_arrive_expect_tx(bar, g.row_bytes);
-        if (g.flags & 4u)
-            bulk_g2s_hint(sm.ring + (size_t)slot * g.row_bytes, g.vectors + (size_t)id * g.row_bytes, g.row_bytes, bar, pol);
-        else
-            bulk_g2s(sm.ring + (size_t)slot * g.row_bytes, g.vectors + (size_t)id * g.row_bytes, g.row_bytes, bar);
+        bulk_g2s(sm.ring + (size_t)slot * g.row_bytes, g.vectors + (size_t)id * g.row_bytes, g.row_bytes, bar);
     }
 
     // distances value -> cand_id[0..n) into cand_d[0..n).  Callers bracket it with __syncthreads().
@@ -274,8 +406,9 @@ template <int DM> struct PqEval : WalkBase {
     float* qbuf; // shared [dims]
     float a2;
 
-    __device__ __forceinline__ void init(const GraphView& gv, uint8_t* smem_raw, const WalkLayout& lay, uint32_t, const SearchScratch& s) {
-        init_base(gv, smem_raw, lay, s);
+    __device__ __forceinline__ explicit PqEval(const GraphView& gv) : WalkBase(gv) {}
+    __device__ __forceinline__ void init(uint8_t* smem_raw, const WalkLayout& lay, uint32_t, const SearchScratch& s) {
+        init_base(smem_raw, lay, s);
         lut = reinterpret_cast<float*>(smem_raw);
         qbuf = lut + (size_t)g.num_subvectors * g.num_centroids;
         a2 = 0.f;
@@ -363,6 +496,7 @@ template <int DM> struct PqEval : WalkBase {
 };
 
 template <class E> struct WalkerT : E {
+    __device__ __forceinline__ explicit WalkerT(const GraphView& gv) : E(gv) {}
     using E::eval;
     using E::g;
     using E::lane;
@@ -442,8 +576,19 @@ template <class E> struct WalkerT : E {
     // the reference re-measures it, so the counter advances).  `skip` = node whose expansion is skipped
     // (index.hpp:3357 new_slot; kNoNeighbor for plain search).  Leaves the ascending top list in shared memory;
     // returns its size (uniform across the CTA).  Visited bits are cleared before returning.
+    // The top list lives in warp 0's registers when L <= 64 (TopRegs) and in shared memory otherwise (TopSmem).
     __device__ __forceinline__ uint32_t beam(int level, uint32_t start, float start_d, uint32_t L, uint32_t skip) {
-        uint32_t size = 0, cursor = 0, ntouched = 0; // warp-0 uniform
+#ifdef LB200_TOPREGS
+        if (L <= TopRegs::kCap)
+            return beam_impl<TopRegs>(level, start, start_d, L, skip);
+#endif
+        return beam_impl<TopSmem>(level, start, start_d, L, skip);
+    }
+
+    template <class Top>
+    __device__ __forceinline__ uint32_t beam_impl(int level, uint32_t start, float start_d, uint32_t L, uint32_t skip) {
+        uint32_t ntouched = 0; // warp-0 uniform
+        Top top;
         // Distance ties at the eviction boundary: the reference's queue keeps an element after `top` evicted it, and still
         // expands it while its distance EQUALS the radius (the stop test index.hpp:3445 is a strict '>').  Such elements
         // wait in `limbo`; they all share one distance (the radius at the time) and die as soon as the radius shrinks.
@@ -451,45 +596,25 @@ template <class E> struct WalkerT : E {
         float limbo_d = 0.f;
         __syncthreads();
         if (warp == 0) {
+            top.init(sm, L, start_d, start, lane);
             if (lane == 0) {
-                sm.top_d[0] = start_d, sm.top_i[0] = start;
                 atomicOr(&vis[start >> 5], 1u << (start & 31));
                 touched[0] = start >> 5;
             }
-            size = 1, cursor = 0, ntouched = 1;
+            ntouched = 1;
             st_dist += 1; // index.hpp:3436 / :3343
             __syncwarp();
         }
         for (;;) {
             __syncthreads(); // (A) insertions of the previous round are complete
             if (warp == 0) {
-                if (cursor >= size && limbo_n == 0) {
+                uint32_t c = kNoNeighbor;
+                if (!top.pop(c, lane) && limbo_n)
+                    c = sm.limbo[--limbo_n]; // distance == radius: not beyond it, so the reference expands it too
+                if (c == kNoNeighbor) {
                     if (lane == 0)
                         sm.ctrl->n = kDone;
                 } else {
-                    uint32_t c;
-                    if (cursor < size) {
-                        c = sm.top_i[cursor];
-                        __syncwarp();
-                        if (lane == 0)
-                            sm.top_i[cursor] = c | kExpandedBit;
-                        __syncwarp();
-                    } else {
-                        c = sm.limbo[--limbo_n]; // distance == radius: not beyond it, so the reference expands it too
-                    }
-                    if (cursor < size) { // advance the cursor to the next unexpanded entry
-                        uint32_t nxt = size;
-                        for (uint32_t b = cursor + 1; b < size; b += 32) {
-                            uint32_t e = b + lane;
-                            bool un = e < size && !(sm.top_i[e] & kExpandedBit);
-                            uint32_t m = __ballot_sync(0xffffffffu, un);
-                            if (m) {
-                                nxt = b + __ffs(m) - 1;
-                                break;
-                            }
-                        }
-                        cursor = nxt;
-                    }
                     uint32_t n = 0;
                     if (c != skip) {
                         uint32_t width;
@@ -540,19 +665,20 @@ template <class E> struct WalkerT : E {
                 for (uint32_t base = 0; base < n; base += 32) {
                     const uint32_t j = base + lane;
                     const float dj = j < n ? sm.cand_d[j] : INFINITY;
-                    uint32_t m = __ballot_sync(0xffffffffu, j < n && (size < L || dj < sm.top_d[size - 1]));
+                    float radius = top.radius(lane);
+                    uint32_t m = __ballot_sync(0xffffffffu, j < n && (top.size < L || dj < radius));
                     while (m) {
                         const int b = __ffs(m) - 1;
                         m &= m - 1;
                         const float d = __shfl_sync(0xffffffffu, dj, b);
-                        if (size < L || d < sm.top_d[size - 1]) {
+                        if (top.size < L || d < radius) {
                             const uint32_t id = sm.cand_id[base + b];
                             float ev_d;
                             uint32_t ev_i;
-                            top_insert(sm.top_d, sm.top_i, size, cursor, L, d, id, lane, ev_d, ev_i);
+                            top.insert(d, id, lane, ev_d, ev_i);
                             if (level == 0 && (g.flags & 2u) && lane == 0)
                                 prefetch_l2(g.adj0 + (size_t)id * g.M0);
-                            const float radius = sm.top_d[size - 1];
+                            radius = top.radius(lane);
                             if (limbo_n && radius < limbo_d)
                                 limbo_n = 0; // the radius shrank below the waiting ties: they can never be expanded
                             if (ev_i != kNoNeighbor && !(ev_i & kExpandedBit) && ev_d == radius && limbo_n < kLimboCap) {
@@ -566,8 +692,11 @@ template <class E> struct WalkerT : E {
                 }
             }
         }
-        if (threadIdx.x == 0)
-            sm.ctrl->ntouched = ntouched, sm.ctrl->top_size = size;
+        if (warp == 0) {
+            top.flush(lane);
+            if (lane == 0)
+                sm.ctrl->ntouched = ntouched, sm.ctrl->top_size = top.size;
+        }
         __syncthreads();
         { // un-visit only the words this walk touched
             const uint32_t nt = sm.ctrl->ntouched;
