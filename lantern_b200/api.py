@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.environ.get("LB200_LIBRARY", os.path.join(HERE, "liblantern_b200.so"))  # LB200_LIBRARY: A/B experiments only
+SO = os.path.join(HERE, "liblantern_b200.so")
 
 METRIC = {"cos": 1, "ip": 2, "l2sq": 3, "hamming": 8}
 SCALAR = {"f32": 1, "f64": 2, "f16": 3, "i8": 4, "b1": 5}

@@ -142,10 +142,10 @@ __device__ __forceinline__ void top_insert(float* td, uint32_t* ti, uint32_t& si
     top_insert(td, ti, size, cursor, L, d, id, lane, ev_d, ev_i);
 }
 
-// ---- the top-`L` list of one walk (warp 0 only).  Two stores with identical semantics ---------------------------
+// ---- the top-`L` list of one walk (warp 0 only) ------------------------------------------------------------------
 // sorted_buffer_gt (index.hpp:668-780): ascending by distance, insert at lower_bound (before equal elements), evict the
 // tail when full; entries carry an "expanded" flag (kExpandedBit) that replaces the reference's separate candidate heap.
-struct TopSmem { // any L: arrays in shared memory
+struct TopSmem { // arrays in shared memory
     float* td;
     uint32_t* ti;
     uint32_t size, cursor, L;
@@ -182,101 +182,6 @@ struct TopSmem { // any L: arrays in shared memory
         top_insert(td, ti, size, cursor, L, d, id, lane, ev_d, ev_i);
     }
     __device__ __forceinline__ void flush(int) {}
-};
-
-struct TopRegs { // L <= 64: element e lives in lane e & 31, register e >> 5 of warp 0
-    static constexpr int kRegs = 2;
-    static constexpr uint32_t kCap = 32 * kRegs;
-    float rd[kRegs];
-    uint32_t ri[kRegs];
-    float* td;
-    uint32_t* ti;
-    uint32_t size, L;
-    __device__ __forceinline__ void init(const WalkSmem& sm, uint32_t cap, float d, uint32_t id, int lane) {
-        td = sm.top_d, ti = sm.top_i, L = cap, size = 1;
-#pragma unroll
-        for (int r = 0; r < kRegs; ++r)
-            rd[r] = INFINITY, ri[r] = kNoNeighbor;
-        if (lane == 0)
-            rd[0] = d, ri[0] = id;
-    }
-    __device__ __forceinline__ bool pop(uint32_t& c, int lane) {
-        bool got = false;
-#pragma unroll
-        for (int r = 0; r < kRegs; ++r) {
-            if (!got && (uint32_t)(r * 32) < size) {
-                const bool un = (uint32_t)(r * 32 + lane) < size && !(ri[r] & kExpandedBit);
-                const uint32_t m = __ballot_sync(0xffffffffu, un);
-                if (m) {
-                    const int l = __ffs(m) - 1;
-                    c = __shfl_sync(0xffffffffu, ri[r], l);
-                    if (lane == l)
-                        ri[r] |= kExpandedBit;
-                    got = true;
-                }
-            }
-        }
-        return got;
-    }
-    __device__ __forceinline__ float get_d(uint32_t e) const {
-        float v = 0.f;
-#pragma unroll
-        for (int r = 0; r < kRegs; ++r)
-            if ((e >> 5) == (uint32_t)r)
-                v = __shfl_sync(0xffffffffu, rd[r], e & 31);
-        return v;
-    }
-    __device__ __forceinline__ uint32_t get_i(uint32_t e) const {
-        uint32_t v = 0;
-#pragma unroll
-        for (int r = 0; r < kRegs; ++r)
-            if ((e >> 5) == (uint32_t)r)
-                v = __shfl_sync(0xffffffffu, ri[r], e & 31);
-        return v;
-    }
-    __device__ __forceinline__ float radius(int) const { return get_d(size - 1); }
-    __device__ __forceinline__ void insert(float d, uint32_t id, int lane, float& ev_d, uint32_t& ev_i) {
-        ev_i = kNoNeighbor, ev_d = 0.f;
-        if (size == L)
-            ev_d = get_d(L - 1), ev_i = get_i(L - 1);
-        uint32_t pos = 0; // lower_bound: entries strictly below d form a prefix
-#pragma unroll
-        for (int r = 0; r < kRegs; ++r)
-            if ((uint32_t)(r * 32) < size)
-                pos += __popc(__ballot_sync(0xffffffffu, (uint32_t)(r * 32 + lane) < size && rd[r] < d));
-        const uint32_t last = (size == L) ? L - 1 : size;
-        float pd[kRegs];
-        uint32_t pi[kRegs];
-#pragma unroll
-        for (int r = 0; r < kRegs; ++r) { // value of element e-1 as seen by the holder of element e
-            pd[r] = __shfl_up_sync(0xffffffffu, rd[r], 1);
-            pi[r] = __shfl_up_sync(0xffffffffu, ri[r], 1);
-            if (r > 0) {
-                const float cd = __shfl_sync(0xffffffffu, rd[r - 1], 31);
-                const uint32_t ci = __shfl_sync(0xffffffffu, ri[r - 1], 31);
-                if (lane == 0)
-                    pd[r] = cd, pi[r] = ci;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < kRegs; ++r) {
-            const uint32_t e = r * 32 + lane;
-            if (e > pos && e <= last)
-                rd[r] = pd[r], ri[r] = pi[r];
-            else if (e == pos)
-                rd[r] = d, ri[r] = id;
-        }
-        size = last + 1;
-    }
-    __device__ __forceinline__ void flush(int lane) {
-#pragma unroll
-        for (int r = 0; r < kRegs; ++r) {
-            const uint32_t e = r * 32 + lane;
-            if (e < size)
-                td[e] = rd[r], ti[e] = ri[r];
-        }
-        __syncwarp();
-    }
 };
 
 // state shared by every evaluator / walker
@@ -576,12 +481,9 @@ template <class E> struct WalkerT : E {
     // the reference re-measures it, so the counter advances).  `skip` = node whose expansion is skipped
     // (index.hpp:3357 new_slot; kNoNeighbor for plain search).  Leaves the ascending top list in shared memory;
     // returns its size (uniform across the CTA).  Visited bits are cleared before returning.
-    // The top list lives in warp 0's registers when L <= 64 (TopRegs) and in shared memory otherwise (TopSmem).
+    // (A register-resident top list for L <= 64 was measured on the B200: 72 registers/thread cost one resident CTA per SM
+    //  and lost 2.5 % at batch 1024 -- the list stays in shared memory.)
     __device__ __forceinline__ uint32_t beam(int level, uint32_t start, float start_d, uint32_t L, uint32_t skip) {
-#ifdef LB200_TOPREGS
-        if (L <= TopRegs::kCap)
-            return beam_impl<TopRegs>(level, start, start_d, L, skip);
-#endif
         return beam_impl<TopSmem>(level, start, start_d, L, skip);
     }
 
