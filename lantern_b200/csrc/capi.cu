@@ -231,6 +231,7 @@ LB200_EXPORT size_t lb200_search_ef(lb200_index_t h, void const* query, lb200_sc
     size_t found = 0;
     guarded(error, [&] {
         Index* idx = as_index(h);
+        std::lock_guard<std::mutex> stream_guard(idx->stream_mu_);
         const size_t qbytes = scalar_row_bytes(kind, idx->config().dims);
         // Streaming (scan.c:240-292 doubles k and passes continue_search=true; index.hpp:3415-3430 then skips what was
         // already returned and resumes from the frontier).  Here the continuation is a fresh search for

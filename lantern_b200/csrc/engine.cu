@@ -70,7 +70,7 @@ Index::Index(const IndexConfig& cfg, const float* codebook) : cfg_(cfg) {
         LB_CUDA(cudaMalloc(&d_pq_pair_, cfg.num_subvectors * cfg.num_centroids * cfg.num_centroids * sizeof(float)));
         LB_CUDA(cudaMalloc(&d_pq_norm_, cfg.num_subvectors * cfg.num_centroids * sizeof(float)));
         launch_pq_tables(d_codebook_, cfg.dims, cfg.num_centroids, cfg.num_subvectors, dist_mode_ == DM_COS, d_pq_pair_, d_pq_norm_, 0);
-        if ((cfg.num_subvectors * cfg.num_centroids + cfg.dims) * 4 > 200 * 1024)
+        if ((cfg.num_subvectors * std::min<size_t>(cfg.num_centroids, 128) + cfg.dims) * 4 > 200 * 1024)
             throw CudaError("pq: num_subvectors * num_centroids look-up table does not fit in shared memory");
     } else {
         stored_bytes_ = vec_bytes_;
@@ -227,6 +227,9 @@ GraphView Index::view() const {
     g.dims = (uint32_t)cfg_.dims;
     g.num_centroids = (uint32_t)cfg_.num_centroids;
     g.num_subvectors = (uint32_t)cfg_.num_subvectors;
+    // the reference's encoder never emits centroid ids >= 128 (signed-char loop, lantern_storage.hpp:123) and neither does
+    // lb200_add*: then half of a 256-entry table can never be addressed and is not built (half the shared memory)
+    g.pq_lut_width = (uint32_t)((cfg_.num_centroids > 128 && pq_max_code_ < 128) ? 128 : cfg_.num_centroids);
     g.flags = 2u; // measured best on B200: L2-prefetch the adjacency line of nodes that enter the top list
     if (const char* e = getenv("LB200_FLAGS"))
         g.flags = (uint32_t)atoi(e);

@@ -56,6 +56,7 @@ struct GraphView {
     const float* pq_norm;  // [nsub][ncent] |centroid slice|^2 (cos)
     uint32_t flags;        // tuning: 1 = L2-prefetch the adjacency of every measured node, 2 = of accepted nodes only
     uint32_t dims, num_centroids, num_subvectors;
+    uint32_t pq_lut_width; // centroids the per-value table covers (= num_centroids, or 128 when every stored code is < 128)
 };
 
 struct SearchScratch {
@@ -125,6 +126,7 @@ class Index {
     float* d_codebook_ = nullptr;
     float* d_pq_pair_ = nullptr;
     float* d_pq_norm_ = nullptr;
+    uint32_t pq_max_code_ = 0; // largest centroid id present in the stored codes
     float* d_pending_raw_ = nullptr; // pq: raw f32 rows of the pending vectors (the value side of build distances)
     size_t pending_raw_cap_ = 0;
     // host mirrors of the small per-node metadata
@@ -146,6 +148,7 @@ class Index {
     // streaming state of the single-query entry point (usearch_search_ef continue_search, scan.c:240-292)
     std::vector<uint8_t> stream_query_;
     std::vector<uint64_t> stream_returned_; // keys handed out so far for stream_query_
+    std::mutex stream_mu_;
 
     void ensure_scratch(uint32_t ctas);
     void* io_buffer(size_t bytes);

@@ -13,6 +13,7 @@
 // The HBM side keeps u32 ids in fixed-width, 0xFFFFFFFF-padded lists; only this file speaks uint48.
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "engine.h"
@@ -181,6 +182,22 @@ void Index::load_buffer(const void* buffer, size_t length) {
         memcpy(rows.data() + i * row_bytes_, p, stored_bytes_);
         p += stored_bytes_;
     }
+    if (n) { // the walk starts at entry_slot on level max_level: both must be consistent or the kernels would read out of bounds
+        if (hdr[4] >= n)
+            throw CudaError("index file: entry slot out of range");
+        if ((int64_t)hdr[3] != (int64_t)levels[hdr[4]])
+            throw CudaError("index file: entry node level differs from max_level");
+        for (size_t i = 0; i < n; ++i) {
+            if (levels[i] > (int16_t)hdr[3])
+                throw CudaError("index file: node above max_level");
+            for (int l = 1; l <= levels[i]; ++l) { // a level-l link must point to a node that exists on level l
+                const uint32_t* list = upper_adj.data() + ((size_t)upper_ref[i] + (l - 1)) * M;
+                for (size_t j = 0; j < M && list[j] != kNoNeighbor; ++j)
+                    if (levels[list[j]] < l)
+                        throw CudaError("index file: link to a node that is missing on that level");
+            }
+        }
+    }
     // commit
     n_ = 0, pending_n_ = 0;
     ensure_capacity(n ? n : 1);
@@ -195,6 +212,16 @@ void Index::load_buffer(const void* buffer, size_t length) {
         if (!upper_adj.empty())
             LB_CUDA(cudaMemcpy(d_upper_adj_, upper_adj.data(), upper_adj.size() * 4, cudaMemcpyHostToDevice));
         LB_CUDA(cudaMemcpy(d_keys_, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice));
+    }
+    if (cfg_.pq) { // codes written by other tools may use all 256 centroids: size the look-up tables accordingly
+        pq_max_code_ = 0;
+        for (size_t i = 0; i < n; ++i)
+            for (size_t s2 = 0; s2 < stored_bytes_; ++s2) {
+                const uint8_t c = rows[i * row_bytes_ + s2];
+                if (c >= cfg_.num_centroids)
+                    throw CudaError("corrupted centroid id"); // lantern_storage.hpp:141
+                pq_max_code_ = std::max<uint32_t>(pq_max_code_, c);
+            }
     }
     upper_lists_ = upper_adj.size() / M;
     h_levels_ = std::move(levels);

@@ -92,7 +92,7 @@ template <class W> int occupancy_one(size_t smem) {
 } // namespace
 
 static size_t search_smem(const GraphView& g, bool pq, uint32_t R, uint32_t L) {
-    return pq ? walk_layout_pq(g.num_subvectors, g.num_centroids, g.dims, L, g.M0).total : walk_layout(R, g.row_bytes, L, g.M0).total;
+    return pq ? walk_layout_pq(g.num_subvectors, g.pq_lut_width, g.dims, L, g.M0).total : walk_layout(R, g.row_bytes, L, g.M0).total;
 }
 
 uint32_t search_max_ctas(int dist_mode, int scalar_kind, const GraphView& g, uint32_t L, bool pq) {

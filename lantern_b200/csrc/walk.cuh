@@ -74,8 +74,8 @@ __host__ __device__ inline WalkLayout walk_layout(uint32_t R, uint32_t row_bytes
     return walk_layout_bytes((size_t)R * row_bytes, R, top_cap, cand_cap);
 }
 // PQ: look-up table [nsub][ncent] + value staging [dims]
-__host__ __device__ inline WalkLayout walk_layout_pq(uint32_t nsub, uint32_t ncent, uint32_t dims, uint32_t top_cap, uint32_t cand_cap) {
-    return walk_layout_bytes(((size_t)nsub * ncent + dims) * 4, 0, top_cap, cand_cap);
+__host__ __device__ inline WalkLayout walk_layout_pq(uint32_t nsub, uint32_t lut_width, uint32_t dims, uint32_t top_cap, uint32_t cand_cap) {
+    return walk_layout_bytes(((size_t)nsub * lut_width + dims) * 4, 0, top_cap, cand_cap);
 }
 
 inline uint32_t pick_ring_slots(uint32_t row_bytes) {
@@ -305,7 +305,7 @@ template <int DM, int SK, int NQ> struct RowEval : WalkBase {
 // [nsub][ncent][ncent] precomputed at index creation.  Code rows (nsub bytes) are read straight from HBM/L2.
 template <int DM> struct PqEval : WalkBase {
     static __host__ __device__ WalkLayout layout(const GraphView& g, uint32_t, uint32_t top_cap, uint32_t cand_cap) {
-        return walk_layout_pq(g.num_subvectors, g.num_centroids, g.dims, top_cap, cand_cap);
+        return walk_layout_pq(g.num_subvectors, g.pq_lut_width, g.dims, top_cap, cand_cap);
     }
     float* lut;  // shared [nsub][ncent]
     float* qbuf; // shared [dims]
@@ -315,7 +315,7 @@ template <int DM> struct PqEval : WalkBase {
     __device__ __forceinline__ void init(uint8_t* smem_raw, const WalkLayout& lay, uint32_t, const SearchScratch& s) {
         init_base(smem_raw, lay, s);
         lut = reinterpret_cast<float*>(smem_raw);
-        qbuf = lut + (size_t)g.num_subvectors * g.num_centroids;
+        qbuf = lut + (size_t)g.num_subvectors * g.pq_lut_width;
         a2 = 0.f;
         __syncthreads();
     }
@@ -323,7 +323,7 @@ template <int DM> struct PqEval : WalkBase {
     // `row` = raw f32 vector (dims floats) in global memory
     __device__ __forceinline__ void load_value(const uint8_t* row) {
         const float* q = reinterpret_cast<const float*>(row);
-        const uint32_t dims = g.dims, ncent = g.num_centroids, nsub = g.num_subvectors, sd = dims / nsub;
+        const uint32_t dims = g.dims, ncent = g.pq_lut_width, nsub = g.num_subvectors, sd = dims / nsub;
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < dims; i += kWalkThreads)
             qbuf[i] = __ldg(q + i);
@@ -354,24 +354,24 @@ template <int DM> struct PqEval : WalkBase {
     }
 
     __device__ __forceinline__ void load_node(uint32_t id) {
-        const uint32_t ncent = g.num_centroids, nsub = g.num_subvectors;
+        const uint32_t ncent = g.pq_lut_width, full = g.num_centroids, nsub = g.num_subvectors;
         const uint8_t* codes = g.vectors + (size_t)id * g.row_bytes;
         __syncthreads();
         for (uint32_t e = threadIdx.x; e < nsub * ncent; e += kWalkThreads) {
             const uint32_t s = e / ncent, c = e - s * ncent;
-            lut[e] = __ldg(g.pq_pair + ((size_t)s * ncent + __ldg(codes + s)) * ncent + c);
+            lut[e] = __ldg(g.pq_pair + ((size_t)s * full + __ldg(codes + s)) * full + c);
         }
         if constexpr (DM == DM_COS) {
             float part = 0.f;
             for (uint32_t s = lane; s < nsub; s += 32)
-                part += __ldg(g.pq_norm + (size_t)s * ncent + __ldg(codes + s));
+                part += __ldg(g.pq_norm + (size_t)s * full + __ldg(codes + s));
             a2 = warp_sum(part);
         }
         __syncthreads();
     }
 
     __device__ __forceinline__ void eval(uint32_t n) {
-        const uint32_t ncent = g.num_centroids, nsub = g.num_subvectors, words = (nsub + 3) / 4;
+        const uint32_t ncent = g.pq_lut_width, full = g.num_centroids, nsub = g.num_subvectors, words = (nsub + 3) / 4;
         for (uint32_t j = warp; j < n; j += kWalkWarps) {
             const uint32_t* row = reinterpret_cast<const uint32_t*>(g.vectors + (size_t)sm.cand_id[j] * g.row_bytes);
             float acc = 0.f, b2 = 0.f;
@@ -384,7 +384,7 @@ template <int DM> struct PqEval : WalkBase {
                         const uint32_t c = (w32 >> (8 * b)) & 255u;
                         acc += lut[s * ncent + c];
                         if constexpr (DM == DM_COS)
-                            b2 += __ldg(g.pq_norm + (size_t)s * ncent + c);
+                            b2 += __ldg(g.pq_norm + (size_t)s * full + c);
                     }
                 }
             }

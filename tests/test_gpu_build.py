@@ -97,3 +97,43 @@ def test_hamming_build(eng):
     truth, td = eng.exact_search(X, Q, 10, "hamming", "b1")
     assert np.array_equal(gd[:, 0], np.zeros(200, np.float32))
     assert np.mean(gd <= td + 1e-6) > 0.9  # distance profile close to exact
+
+
+@pytest.mark.parametrize("quant,scale", [("f16", 1.0), ("i8", 0.3)])
+def test_scalar_quantised_builds(eng, port, quant, scale):
+    """quant_bits=16 / 8 storage: the GPU build works in the storage domain like the reference (f32 in, cast on add)."""
+    n, d = 6000, 48
+    X = structured(n, d, seed=13) * scale
+    Q = structured(200, d, seed=14) * scale
+    g = eng.Index(d, "cos", quant, M=16, efc=64, ef=64)
+    g.reserve(n)
+    g.add_batch(np.arange(1, n + 1, dtype=np.uint64), X)
+    g.build()
+    gk, gd, _ = g.search_batch(Q, 10)
+    # ground truth in the same storage domain
+    cx, cq = eng.cast(X, quant), eng.cast(Q, quant)
+    tk, td = eng.exact_search(cx, cq, 10, "cos", quant, d)
+    assert recall(gk - 1, tk) > 0.9
+    # the GPU-built file loads into the oracle and gives (nearly) the same answers there
+    p = port.PortIndex(d, "cos", quant, M=16, efc=64, ef=64)
+    p.reserve(n)
+    p.load_buffer(g.save_buffer())
+    pk, pd, _, _ = p.search_batch(Q[:60], 10)
+    assert np.mean(pk == gk[:60]) > 0.97 and np.allclose(pd, gd[:60], rtol=1e-4, atol=1e-5)
+
+
+def test_malformed_index_files_are_rejected(eng, port):
+    X = structured(300, 16, seed=2)
+    pidx = build_port_index(port, X, "l2sq", "f32", M=4, efc=32, ef=16)
+    buf = pidx.save_buffer().copy()
+    g = eng.Index(16, "l2sq", "f32", M=4, efc=32, ef=16)
+    bad = buf.copy(); bad[112:118] = 255  # entry slot far out of range
+    with pytest.raises(eng.EngineError, match="entry slot"):
+        g.load_buffer(bad)
+    bad = buf.copy(); bad[104] = 9  # max_level that no node has
+    with pytest.raises(eng.EngineError, match="max_level|level"):
+        g.load_buffer(bad)
+    with pytest.raises(eng.EngineError, match="truncated"):
+        g.load_buffer(buf[:len(buf) // 2])
+    g.load_buffer(buf)  # the intact file still loads afterwards
+    assert g.size() == 300
