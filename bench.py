@@ -274,6 +274,7 @@ def run_ours(args, wl):
     pq = wl.get("pq")
     stream = torch.cuda.current_stream()
     nrec = min(B, 1024)
+    expand = max(1, args.search_expand)
     t0 = time.perf_counter()
     Q = gen_t(pool * B, dim, SEED_QUERY, dev)
     ef_shard = args.shard_ef if (world > 1 and args.shard_ef > 0) else ef
@@ -333,6 +334,8 @@ def run_ours(args, wl):
         pq_info = {"num_subvectors": nsub, "num_centroids": ncent, "kmeans_rounds": rounds, "kmeans_seconds": t_train,
                    "codebook": "trained by lb200_train_pq_device on 200k rows, compat128 encode (reference quirk)"}
 
+    if expand > 1:
+        idx.set_option("search_expand", expand)
     out_keys = torch.empty((B, k), dtype=torch.int64, device=dev)
     out_dists = torch.empty((B, k), dtype=torch.float32, device=dev)
     out_counts = torch.empty((B,), dtype=torch.int32, device=dev)
@@ -643,7 +646,7 @@ def run_ours(args, wl):
             "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "u8 (popcount)" if kind == "b1" else "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "corpus_rows": n, "rows_per_gpu": hi - lo, "ef": ef, "ef_per_shard": ef_shard, "k": k,
+            "config": {"workload": wl["desc"], "corpus_rows": n, "rows_per_gpu": hi - lo, "ef": ef, "ef_per_shard": ef_shard, "k": k, "search_order": "exact (reference order)" if expand == 1 else "relaxed: %d candidates per round" % expand,
                        "batch": B, "parallelism": "row-range shards x%d + NCCL all-gather of top-k + merge" % world if world > 1 else "1 GPU",
                        "l2_policy": "inputs larger than L2: %.1f GB corpus gathered at random; %d distinct query batches cycled" % ((hi - lo) * rowb / 1e9, pool),
                        "generator": ("64 random prototypes XOR 10%% bit flips, seeds %d/%d/%d" % (SEED_P, SEED_CORPUS, SEED_QUERY)) if kind == "b1" else
@@ -673,6 +676,7 @@ def main():
     ap.add_argument("--replicated-comparison", action="store_true", help="--gpus > 1: force the replicated comparison")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="bound on the cpu_baseline search time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--search-expand", type=int, default=1, help="candidates expanded per search round (1 = the reference's exact order)")
     ap.add_argument("--pq-ref-rows", type=int, default=100_000, help="pq workloads: rows the reference indexes for cpu_baseline")
     ap.add_argument("--ref-seconds", type=float, default=60.0, help="--impl reference: target duration of the K timed steps")
     ap.add_argument("--ref-build-seconds", type=float, default=75.0, help="--impl reference: budget for the reference's own build")

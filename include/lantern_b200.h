@@ -145,7 +145,10 @@ LB200_EXPORT void lb200_build(lb200_index_t, lb200_error_t* error);
 /* Engine knobs that have no counterpart in usearch_init_options_t:
  *   "build_batch"  max vectors inserted concurrently per batch (default 0 = one per resident CTA); 1 = strictly sequential insertion,
  *                  i.e. the reference's order of operations (byte-identical graphs on order-independent data);
- *   "build_ratio"  a batch never exceeds (nodes already in the graph) / build_ratio (default 64). */
+ *   "build_ratio"  a batch never exceeds (nodes already in the graph) / build_ratio (default 64);
+ *   "search_expand" candidates expanded per search round (default 1 = the reference's exact order; 2..8 = relaxed order:
+ *                  fewer serial rounds, slightly more distance evaluations, identical results at ef >= N and recall within
+ *                  the +-0.5 % window otherwise). */
 LB200_EXPORT void lb200_set_option(lb200_index_t, char const* name, size_t value, lb200_error_t* error);
 
 /* ---- search path: usearch.h:277-296, lib.cpp:389-410 ------------------------------------------ */

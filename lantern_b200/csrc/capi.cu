@@ -221,6 +221,8 @@ LB200_EXPORT void lb200_set_option(lb200_index_t h, char const* name, size_t val
             idx->build_batch_ = value;
         else if (n == "build_ratio")
             idx->build_ratio_ = value ? value : 1;
+        else if (n == "search_expand")
+            idx->search_expand_ = value ? value : 1;
         else
             throw CudaError("unknown option");
     });

@@ -279,7 +279,8 @@ void Index::search_device(const void* d_queries, size_t nq, size_t stride, int k
     uint8_t* qbuf = query_buffer(nq * qrow);
     launch_cast_rows(d_queries, stride, kind, qbuf, qrow, cfg_.pq ? (int)SK_F32 : cfg_.scalar_kind, cfg_.dims, nq, stream);
 
-    const uint32_t max_ctas = search_max_ctas(dist_mode_, cfg_.scalar_kind, view(), (uint32_t)L, cfg_.pq);
+    const uint32_t expand = (uint32_t)std::min<size_t>(std::max<size_t>(search_expand_, 1), 8);
+    const uint32_t max_ctas = search_max_ctas(dist_mode_, cfg_.scalar_kind, view(), (uint32_t)L, cfg_.pq, expand);
     ensure_scratch(max_ctas);
     LB_CUDA(cudaMemsetAsync(scratch_.counters, 0, 4 * sizeof(unsigned long long), stream));
 
@@ -290,6 +291,7 @@ void Index::search_device(const void* d_queries, size_t nq, size_t stride, int k
     p.queries = qbuf;
     p.query_stride = (uint32_t)qrow;
     p.nq = (uint32_t)nq, p.k = (uint32_t)k, p.L = (uint32_t)L;
+    p.expand = expand;
     p.out_keys = d_keys, p.out_dists = d_dists, p.out_counts = d_counts;
     LB_CUDA(cudaEventRecord(ev0_, stream));
     launch_search(dist_mode_, cfg_.scalar_kind, cfg_.pq, p, stream);

@@ -113,6 +113,7 @@ class Index {
     uint32_t level_rng_ = 1u;   // minstd_rand0 state, default seed (std::default_random_engine, index.hpp:2082)
     size_t build_batch_ = 0;    // max nodes inserted per batch; 0 = one per resident CTA; 1 = the reference's sequential order
     size_t build_ratio_ = 64;   // a batch never exceeds (visible nodes) / build_ratio_
+    size_t search_expand_ = 1;  // 1 = exact-order search; 2..4 = relaxed order (see walk.cuh)
     double last_build_ms_ = 0;
     uint64_t last_build_dist_ = 0;
 
@@ -173,11 +174,12 @@ struct SearchLaunch {
     const uint8_t* queries; // storage kind, stride = query_stride
     uint32_t query_stride;
     uint32_t nq, k, L;
+    uint32_t expand; // candidates expanded per round (1 = the reference's exact order)
     uint64_t* out_keys;
     float* out_dists;
     uint32_t* out_counts;
 };
-uint32_t search_max_ctas(int dist_mode, int scalar_kind, const GraphView& g, uint32_t L, bool pq);
+uint32_t search_max_ctas(int dist_mode, int scalar_kind, const GraphView& g, uint32_t L, bool pq, uint32_t expand);
 void launch_search(int dist_mode, int scalar_kind, bool pq, const SearchLaunch& p, cudaStream_t stream);
 // exact.cu
 void launch_exact(int dist_mode, int scalar_kind, const uint8_t* d_data, size_t n, size_t data_stride,

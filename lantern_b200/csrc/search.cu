@@ -29,7 +29,7 @@ namespace {
 template <class W>
 __global__ void __launch_bounds__(kWalkThreads) hnsw_search_kernel(const __grid_constant__ SearchLaunch p, const uint32_t R) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    const WalkLayout lay = W::layout(p.g, R, p.L, p.g.M0);
+    const WalkLayout lay = W::layout(p.g, R, p.L, p.g.M0 * p.expand);
     W w(p.g);
     w.init(smem_raw, lay, R, p.s);
     WalkSmem& sm = w.sm;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kWalkThreads) hnsw_search_kernel(const __grid_
         uint32_t cur = p.g.entry;
         float cur_d = w.measure_one(cur);
         w.greedy(cur, cur_d, p.g.max_level, 0);
-        const uint32_t size = w.beam(0, cur, cur_d, p.L, kNoNeighbor);
+        const uint32_t size = w.beam(0, cur, cur_d, p.L, kNoNeighbor, p.expand);
 
         // results: top is ascending; shrink(k); keys (index.hpp:2722-2723, 2426-2433)
         if (w.warp == 0) {
@@ -91,16 +91,17 @@ template <class W> int occupancy_one(size_t smem) {
 
 } // namespace
 
-static size_t search_smem(const GraphView& g, bool pq, uint32_t R, uint32_t L) {
-    return pq ? walk_layout_pq(g.num_subvectors, g.pq_lut_width, g.dims, L, g.M0).total : walk_layout(R, g.row_bytes, L, g.M0).total;
+static size_t search_smem(const GraphView& g, bool pq, uint32_t R, uint32_t L, uint32_t expand) {
+    return pq ? walk_layout_pq(g.num_subvectors, g.pq_lut_width, g.dims, L, g.M0 * expand).total
+              : walk_layout(R, g.row_bytes, L, g.M0 * expand).total;
 }
 
-uint32_t search_max_ctas(int dist_mode, int scalar_kind, const GraphView& g, uint32_t L, bool pq) {
+uint32_t search_max_ctas(int dist_mode, int scalar_kind, const GraphView& g, uint32_t L, bool pq, uint32_t expand) {
     const uint32_t R = pick_ring_slots(g.row_bytes);
     const int nq = pq ? 1 : pick_nq(g.row_bytes);
     if (nq < 0)
         throw CudaError("search: vectors wider than 8192 bytes are not supported");
-    const size_t smem = search_smem(g, pq, R, L);
+    const size_t smem = search_smem(g, pq, R, L, expand);
     int occ = 0;
     dispatch_walker(pq, dist_mode, scalar_kind, nq, [&](auto tag) { occ = occupancy_one<typename decltype(tag)::type>(smem); });
     if (occ < 1)
@@ -111,7 +112,7 @@ uint32_t search_max_ctas(int dist_mode, int scalar_kind, const GraphView& g, uin
 void launch_search(int dist_mode, int scalar_kind, bool pq, const SearchLaunch& p, cudaStream_t stream) {
     const uint32_t R = pick_ring_slots(p.g.row_bytes);
     const int nq = pq ? 1 : pick_nq(p.g.row_bytes);
-    const size_t smem = search_smem(p.g, pq, R, p.L);
+    const size_t smem = search_smem(p.g, pq, R, p.L, p.expand);
     const uint32_t grid = p.s.ctas < p.nq ? p.s.ctas : p.nq;
     dispatch_walker(pq, dist_mode, scalar_kind, nq,
                     [&](auto tag) { launch_one<typename decltype(tag)::type>(p, R, smem, grid, stream); });
