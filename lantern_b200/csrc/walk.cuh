@@ -261,6 +261,20 @@ template <int DM, int SK, int NQ> struct RowEval : WalkBase {
         bulk_g2s(sm.ring + (size_t)slot * g.row_bytes, g.vectors + (size_t)id * g.row_bytes, g.row_bytes, bar);
     }
 
+    __device__ __forceinline__ float row_distance(const uint4* row) const {
+        DistAcc<DM, SK> acc;
+        acc.reset();
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            uint32_t c = lane + 32 * i;
+            if (c < nchunks) {
+                uint4 r = row[c];
+                accum_chunk<DM, SK>(acc, qreg[i], r);
+            }
+        }
+        return finish_distance<DM, SK>(acc, a2);
+    }
+
     // distances value -> cand_id[0..n) into cand_d[0..n).  Callers bracket it with __syncthreads().
     __device__ __forceinline__ void eval(uint32_t n) {
         const uint32_t T = n > (uint32_t)warp ? (n - warp + kWalkWarps - 1) / kWalkWarps : 0;
@@ -271,18 +285,7 @@ template <int DM, int SK, int NQ> struct RowEval : WalkBase {
             const uint32_t slot = warp + kWalkWarps * si;
             mbar_wait(&sm.full[slot], (phase_bits >> si) & 1u);
             phase_bits ^= 1u << si;
-            const uint4* row = reinterpret_cast<const uint4*>(sm.ring + (size_t)slot * g.row_bytes);
-            DistAcc<DM, SK> acc;
-            acc.reset();
-#pragma unroll
-            for (int i = 0; i < NQ; ++i) {
-                uint32_t c = lane + 32 * i;
-                if (c < nchunks) {
-                    uint4 r = row[c];
-                    accum_chunk<DM, SK>(acc, qreg[i], r);
-                }
-            }
-            float d = finish_distance<DM, SK>(acc, a2);
+            const float d = row_distance(reinterpret_cast<const uint4*>(sm.ring + (size_t)slot * g.row_bytes));
             if (lane == 0)
                 sm.cand_d[warp + kWalkWarps * t] = d;
             __syncwarp();
