@@ -85,8 +85,8 @@ inline uint32_t pick_ring_slots(uint32_t row_bytes) {
     uint32_t r = (budget / row_bytes) & ~3u;
     if (r < 4)
         r = 4;
-    if (r > 32)
-        r = 32;
+    if (r > 16) // narrow rows: more resident CTAs beat deeper rings (768-byte rows: 16 slots +15 % over 32, profiles/)
+        r = 16;
     return r;
 }
 
