@@ -187,8 +187,7 @@ def run_reference(args, wl):
         return
     from oracle import reflib
     if not reflib.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liboracle_usearch.so missing (run oracle/Makefile)"}))
-        return
+        return run_reference_port(args, wl)
     cores = reflib.lib().refx_hardware_threads()
     # bounded sample: a prefix of the corpus the reference can index in about `--ref-build-seconds` with all cores;
     # the rate is measured on a pilot of 20k rows (it only falls slowly, ~log N, afterwards)
@@ -243,6 +242,40 @@ def run_reference(args, wl):
         "build_vectors_per_s": n_ref / t_build,
     }
     print(json.dumps(line))
+
+
+def run_reference_port(args, wl):
+    """oracle/_ref is not built: time the plain-C restatement of the reference (oracle/hnsw_oracle.c, single thread) on a
+    small bounded sample instead."""
+    from oracle import portlib
+    gen = bits_np if wl.get("kind") == "b1" else structured_np
+    n_ref = min(wl["n"], args.ref_rows or 20_000)
+    X = gen(n_ref, wl["dim"], SEED_CORPUS)
+    per_step = min(wl["batch"], 64)
+    Q = gen((args.steps + args.warmup) * per_step, wl["dim"], SEED_QUERY)
+    idx = portlib.PortIndex(wl["dim"], wl["metric"], wl.get("kind", "f32"), M=wl["M"], efc=wl["efc"], ef=wl["ef"])
+    idx.reserve(n_ref)
+    t0 = time.perf_counter()
+    for i in range(n_ref):
+        idx.add(i + 1, X[i])
+    t_build = time.perf_counter() - t0
+    times = []
+    for s in range(args.steps + args.warmup):
+        t0 = time.perf_counter()
+        idx.search_batch(Q[s * per_step:(s + 1) * per_step], wl["k"])
+        if s >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    value = args.steps * per_step / sum(times)
+    sample = "oracle PORT (oracle/_ref missing): 1 thread, own graph over the first %d rows (%.0f s), %d queries per step" % (
+        n_ref, t_build, per_step)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8 (popcount)" if wl.get("kind") == "b1" else "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "corpus_rows_indexed": n_ref, "ef": wl["ef"], "k": wl["k"], "batch": wl["batch"],
+                   "queries_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 # --------------------------------------------------------------------------------------- our arm
@@ -641,6 +674,20 @@ def run_ours(args, wl):
                       "reference_computed_distances": int(comp0), "engine_computed_distances": int(st0["computed_distances"]),
                       "reference_recall_at_10": recall_at_k(rk0[:nrec], truth)}
 
+    if world == 1 and not args.no_cpu_baseline and cpu_baseline is None and not pq:
+        # oracle/_ref unavailable (or the index file too large for host RAM): the plain-C restatement on one core, on a
+        # bounded sample of the same queries; it loads the engine's index file when that is small enough, else skips
+        from oracle import portlib
+        if n * rowb <= 2e9:
+            pidx = portlib.PortIndex(dim, wl["metric"], kind, M=wl["M"], efc=wl["efc"], ef=ef)
+            pidx.reserve(n)
+            pidx.load_buffer(idx.save_buffer())
+            qh = Q[:256].cpu().numpy()
+            t0 = time.perf_counter()
+            pidx.search_batch(qh, k)
+            dt = time.perf_counter() - t0
+            cpu_baseline = {"value": len(qh) / dt, "unit": "queries/s", "cores": 1, "kind": "port",
+                            "sample": "oracle port (hnsw_oracle.c, 1 thread) loads the engine's index file and searches %d queries" % len(qh)}
     if rank == 0:
         line = {
             "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
