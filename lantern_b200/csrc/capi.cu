@@ -195,7 +195,7 @@ LB200_EXPORT void lb200_add(lb200_index_t h, lb200_key_t key, void const* vector
         Index* idx = as_index(h);
         if (idx->size() >= idx->capacity())
             throw CudaError("Reserve capacity ahead of insertions!"); // index.hpp:2514-2517
-        idx->add_host(&key, vector, 1, scalar_row_bytes(kind, idx->config().dims), kind);
+        idx->add_one_host(key, vector, kind);
     });
 }
 

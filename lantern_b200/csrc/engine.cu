@@ -203,7 +203,44 @@ void Index::add_host(const uint64_t* keys, const void* vectors, size_t n, size_t
     LB_CUDA(cudaDeviceSynchronize());
 }
 
+// usearch_add (U/c/lib.cpp:357-365) arrives one row at a time from Lantern's heap scan (build.c:83-140): rows are staged on
+// the host and handed to the device 4096 at a time; every consumer of the index flushes first.
+void Index::add_one_host(uint64_t key, const void* vector, int kind) {
+    check_input_kind(cfg_, kind);
+    if (key == ~0ull)
+        throw CudaError("key UINT64_MAX is reserved (free key)");
+    const size_t in_bytes = scalar_row_bytes(kind, cfg_.dims);
+    bool full = false;
+    {
+        std::lock_guard<std::mutex> g(stage_mu_);
+        if (!staged_keys_.empty() && staged_kind_ != kind)
+            throw CudaError("vectors of one index must all be passed in the same scalar kind");
+        staged_kind_ = kind;
+        staged_keys_.push_back(key);
+        const uint8_t* p = (const uint8_t*)vector;
+        staged_rows_.insert(staged_rows_.end(), p, p + in_bytes);
+        full = staged_keys_.size() >= 4096;
+    }
+    if (full)
+        flush_staged();
+}
+
+void Index::flush_staged() {
+    std::vector<uint8_t> rows;
+    std::vector<uint64_t> keys;
+    int kind;
+    {
+        std::lock_guard<std::mutex> g(stage_mu_);
+        if (staged_keys_.empty())
+            return;
+        rows.swap(staged_rows_), keys.swap(staged_keys_);
+        kind = staged_kind_;
+    }
+    add_host(keys.data(), rows.data(), keys.size(), scalar_row_bytes(kind, cfg_.dims), kind);
+}
+
 void Index::build() {
+    flush_staged();
     std::lock_guard<std::mutex> g(mu_);
     if (pending_n_)
         build_pending(*this);
@@ -255,6 +292,7 @@ void Index::ensure_scratch(uint32_t ctas) {
 
 void Index::search_device(const void* d_queries, size_t nq, size_t stride, int kind, size_t k, size_t ef, uint64_t* d_keys,
                           float* d_dists, uint32_t* d_counts, cudaStream_t stream) {
+    flush_staged();
     std::lock_guard<std::mutex> g(mu_);
     check_input_kind(cfg_, kind);
     if (!nq || !k)

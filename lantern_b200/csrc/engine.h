@@ -74,7 +74,7 @@ class Index {
     ~Index();
 
     const IndexConfig& config() const { return cfg_; }
-    size_t size() const { return n_ + pending_n_; }
+    size_t size() const { return n_ + pending_n_ + staged_keys_.size(); }
     size_t capacity() const { return capacity_; }
     size_t row_bytes() const { return row_bytes_; }
 
@@ -82,6 +82,8 @@ class Index {
     // staging (host or device source) of vectors in the *input* kind (f32 or b1)
     void add_host(const uint64_t* keys, const void* vectors, size_t n, size_t stride, int kind);
     void add_device(const uint64_t* host_keys, const void* d_vectors, size_t n, size_t stride, int kind);
+    void add_one_host(uint64_t key, const void* vector, int kind); // usearch_add: staged on the host, flushed in blocks
+    void flush_staged();                                           // caller holds no lock
     void build(); // insert all pending vectors (build.cu)
 
     // search: queries in device memory, input kind f32 or b1
@@ -136,6 +138,11 @@ class Index {
 
     // pending (not yet inserted) vectors live directly in d_vectors_[n_ ...); only bookkeeping here
     size_t pending_n_ = 0;
+    // vectors added one at a time (usearch_add, build.c:128) wait here until a block is worth a host->device copy
+    std::vector<uint8_t> staged_rows_;
+    std::vector<uint64_t> staged_keys_;
+    int staged_kind_ = 0;
+    std::mutex stage_mu_;
 
     // search scratch
     SearchScratch scratch_{};

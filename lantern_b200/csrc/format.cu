@@ -75,6 +75,7 @@ const uint8_t* get_list(const uint8_t* p, uint32_t* ids, size_t width, size_t n_
 } // namespace
 
 size_t Index::serialized_length() {
+    flush_staged();
     std::lock_guard<std::mutex> g(mu_);
     if (pending_n_)
         build_pending(*this);
@@ -131,6 +132,10 @@ size_t Index::save_buffer(void* buffer, size_t length) {
 
 // usearch_load_buffer / usearch_view_buffer (U/c/lib.cpp:295-313): replaces the index contents.
 void Index::load_buffer(const void* buffer, size_t length) {
+    {
+        std::lock_guard<std::mutex> sg(stage_mu_); // loading replaces the contents, staged rows included
+        staged_rows_.clear(), staged_keys_.clear();
+    }
     std::lock_guard<std::mutex> g(mu_);
     const uint8_t* p = (const uint8_t*)buffer;
     if (length < 136 || memcmp(p, "usearch", 7) != 0)

@@ -137,3 +137,19 @@ def test_malformed_index_files_are_rejected(eng, port):
         g.load_buffer(buf[:len(buf) // 2])
     g.load_buffer(buf)  # the intact file still loads afterwards
     assert g.size() == 300
+
+
+def test_row_at_a_time_adds_are_staged(eng):
+    """usearch_add from a heap scan (build.c:128): one row per call; rows reach the GPU in blocks, size() counts them."""
+    X = structured(5000, 16, seed=61)
+    g = eng.Index(16, "l2sq", "f32", M=8, efc=32, ef=32)
+    g.reserve(5000)
+    for i in range(5000):
+        g.add(i + 1, X[i])
+    assert g.size() == 5000
+    k, d = g.search(X[4999], 1)  # the last, still host-staged row must be findable: search flushes and builds
+    assert k[0] == 5000 and d[0] == 0
+    buf = g.save_buffer()
+    g2 = eng.Index(16, "l2sq", "f32", M=8, efc=32, ef=32)
+    g2.load_buffer(buf)
+    assert g2.size() == 5000

@@ -150,3 +150,34 @@ def test_continue_search_streaming(eng, port):
     other = structured(1, 24, seed=33)[0]
     L.lb200_search_ef(g.h, other.ctypes.data, 1, 5, 0, True, keys.ctypes.data, dists.ctypes.data, C.byref(err))
     assert err.value and b"continue_search" in err.value
+
+
+def test_wide_beam_touched_list_overflow_and_large_k(eng, port):
+    """ef far above the touched-word list (16 Ki entries) exercises the full-bitmap clear; k = 500 the large top list."""
+    rng = np.random.default_rng(41)
+    X = rng.standard_normal((30000, 8)).astype(np.float32)
+    Q = rng.standard_normal((24, 8)).astype(np.float32)
+    pidx = build_port_index(port, X, "l2sq", "f32", M=8, efc=32, ef=32)
+    g = eng.Index(8, "l2sq", "f32", M=8, efc=32, ef=32)
+    g.load_buffer(pidx.save_buffer())
+    for rep in range(2):  # second pass: the bitmaps must have been cleaned by the first
+        gk, gd, gc = g.search_batch(Q, 500, ef=4000)
+        st = g.last_stats()
+        assert st["computed_distances"] / len(Q) > 16384  # the overflow path really ran
+        pk, pd, pc, _ = pidx.search_batch(Q, 500, ef=4000)
+        assert np.array_equal(gc.astype(np.int64), pc) and np.allclose(gd, pd, rtol=1e-5, atol=1e-6)
+        assert np.mean(gk == pk) > 0.995
+    gk2, gd2, _ = g.search_batch(Q, 10)  # and a normal search afterwards still agrees with the oracle
+    pk2, pd2, _, _ = pidx.search_batch(Q, 10)
+    assert np.array_equal(gk2, pk2)
+
+
+def test_high_connectivity_graph(eng, port):
+    X = structured(1500, 24, seed=51)
+    Q = structured(50, 24, seed=52)
+    pidx = build_port_index(port, X, "cos", "f32", M=64, efc=96, ef=80)  # M0 = 128: adjacency spans several 32-id chunks
+    g = eng.Index(24, "cos", "f32", M=64, efc=96, ef=80)
+    g.load_buffer(pidx.save_buffer())
+    gk, gd, _ = g.search_batch(Q, 20)
+    pk, pd, _, _ = pidx.search_batch(Q, 20)
+    assert np.allclose(gd, pd, rtol=1e-5, atol=1e-6) and np.mean(gk == pk) > 0.99
