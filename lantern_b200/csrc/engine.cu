@@ -342,6 +342,7 @@ void Index::search_host(const void* queries, size_t nq, size_t stride, int kind,
     if (!nq || !k)
         return;
     check_input_kind(cfg_, kind);
+    flush_staged(); // before the io buffer holds the queries: flushing stages rows through the same buffer
     const size_t in_bytes = scalar_row_bytes(kind, cfg_.dims);
     uint8_t* base = nullptr;
     size_t o_keys, o_dists, o_counts;
