@@ -275,7 +275,7 @@ GraphView Index::view() const {
 
 void Index::ensure_scratch(uint32_t ctas) {
     const size_t words = round_up((capacity_ + 31) / 32, 32);
-    if (ctas <= scratch_.ctas && words <= scratch_.words_per_cta)
+    if (ctas <= scratch_.ctas && words <= scratch_.words_per_cta && scratch_.touched_cap == touched_cap_)
         return;
     if (scratch_.visited)
         LB_CUDA(cudaFree(scratch_.visited));
@@ -284,7 +284,7 @@ void Index::ensure_scratch(uint32_t ctas) {
     scratch_.visited = nullptr, scratch_.touched = nullptr;
     scratch_.ctas = std::max(ctas, scratch_.ctas);
     scratch_.words_per_cta = words;
-    scratch_.touched_cap = 16384;
+    scratch_.touched_cap = touched_cap_;
     LB_CUDA(cudaMalloc(&scratch_.visited, (size_t)scratch_.ctas * words * sizeof(uint32_t)));
     LB_CUDA(cudaMemset(scratch_.visited, 0, (size_t)scratch_.ctas * words * sizeof(uint32_t)));
     LB_CUDA(cudaMalloc(&scratch_.touched, (size_t)scratch_.ctas * scratch_.touched_cap * sizeof(uint32_t)));

@@ -115,6 +115,7 @@ class Index {
     uint32_t level_rng_ = 1u;   // minstd_rand0 state, default seed (std::default_random_engine, index.hpp:2082)
     size_t build_batch_ = 0;    // max nodes inserted per batch; 0 = one per resident CTA; 1 = the reference's sequential order
     size_t build_ratio_ = 64;   // a batch never exceeds (visible nodes) / build_ratio_
+    uint32_t touched_cap_ = 16384; // per-CTA log of bitmap words to un-visit; beyond it the whole bitmap is cleared
     size_t search_expand_ = 1;  // 1 = exact-order search; 2..4 = relaxed order (see walk.cuh)
     double last_build_ms_ = 0;
     uint64_t last_build_dist_ = 0;

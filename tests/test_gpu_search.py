@@ -153,17 +153,19 @@ def test_continue_search_streaming(eng, port):
 
 
 def test_wide_beam_touched_list_overflow_and_large_k(eng, port):
-    """ef far above the touched-word list (16 Ki entries) exercises the full-bitmap clear; k = 500 the large top list."""
+    """A beam that visits more nodes than the per-CTA un-visit log holds exercises the full-bitmap clear; k = 500 the
+    large top list."""
     rng = np.random.default_rng(41)
     X = rng.standard_normal((30000, 8)).astype(np.float32)
     Q = rng.standard_normal((24, 8)).astype(np.float32)
     pidx = build_port_index(port, X, "l2sq", "f32", M=8, efc=32, ef=32)
     g = eng.Index(8, "l2sq", "f32", M=8, efc=32, ef=32)
     g.load_buffer(pidx.save_buffer())
+    g.set_option("touched_cap", 1024)
     for rep in range(2):  # second pass: the bitmaps must have been cleaned by the first
         gk, gd, gc = g.search_batch(Q, 500, ef=4000)
         st = g.last_stats()
-        assert st["computed_distances"] / len(Q) > 16384  # the overflow path really ran
+        assert st["computed_distances"] / len(Q) > 1024  # the overflow path really ran
         pk, pd, pc, _ = pidx.search_batch(Q, 500, ef=4000)
         assert np.array_equal(gc.astype(np.int64), pc) and np.allclose(gd, pd, rtol=1e-5, atol=1e-6)
         assert np.mean(gk == pk) > 0.995
