@@ -128,3 +128,21 @@ def test_sharded_search_two_ranks_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+REF_HEADER_DIR = "/root/reference/lantern_hnsw/third_party/usearch/c"
+
+
+def test_source_level_drop_in_with_the_reference_header(tmp_path):
+    """A C caller written against the reference's own usearch.h compiles unchanged and links against liblantern_b200.so
+    (what replacing U/c/lib.cpp in lantern.so amounts to, INTEGRATION.md 1).  Runs the cube when a GPU is present;
+    without one the library must report that through the usearch error convention (exit code 3)."""
+    if not os.path.exists(os.path.join(REF_HEADER_DIR, "usearch.h")):
+        pytest.skip("reference header not available on this machine")
+    exe = tmp_path / "dropin"
+    lib_dir = os.path.join(ROOT, "lantern_b200")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", REF_HEADER_DIR, os.path.join(ROOT, "tests", "c", "dropin_usearch_h.c"),
+                           "-o", str(exe), "-L", lib_dir, "-llantern_b200", "-Wl,-rpath," + lib_dir])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    from lantern_b200 import api
+    assert r.returncode == (0 if api.device_count() > 0 else 3), (r.returncode, r.stdout, r.stderr)
