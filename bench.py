@@ -299,7 +299,7 @@ def run_ours(args, wl):
     rowb = dim // 8 if kind == "b1" else dim * 4  # bytes of one input row
     gen_t = bits_torch if kind == "b1" else structured_torch
     nsteps = args.steps + args.warmup
-    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    args.warmup = max(3, args.warmup)  # timing rules: at least 3 warm-up steps (the JSON line reports the value used)
     pool = min(nsteps, args.query_pool)  # distinct query batches, cycled: step s uses batch s % pool
 
     # ---- corpus shard of this rank: contiguous row range ----
@@ -521,7 +521,6 @@ def run_ours(args, wl):
     ev[1].record(stream)
     barrier()
     ms = ev[0].elapsed_time(ev[1])
-    clocks = sampler.stop() if sampler else None
     launches = api.kernel_launches() - launches0
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -537,6 +536,16 @@ def run_ours(args, wl):
                                 out_counts.data_ptr(), stream.cuda_stream)
         st = idx.last_stats()
         alg_bytes += st["algorithmic_bytes"]; kern_ms += st["kernel_ms"]; n_dist += st["computed_distances"]; pops += st["base_pops"]
+    # The clock sampler (nvidia-smi, 20 ms period, ~0.1 s to start) covers the timed region, this pass over the same steps
+    # and -- when both together are shorter than 0.6 s -- further untimed repetitions of the same steps, so that even short
+    # runs (small --steps) yield samples taken under the benchmark's own load.  `ms` is identical on all ranks.
+    extra = int(np.ceil(max(0.0, 600.0 - 2.0 * ms) / max(ms / args.steps, 1e-3)))
+    for s in range(extra):
+        step_device(args.warmup + s)
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["sampled_over"] = "timed steps + stats pass + %d identical untimed steps" % extra
     peak, peak_src = peaks()
     achieved = alg_bytes / (kern_ms / 1e3) / 1e9
     traffic = None

@@ -146,3 +146,22 @@ def test_source_level_drop_in_with_the_reference_header(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     from lantern_b200 import api
     assert r.returncode == (0 if api.device_count() > 0 else 3), (r.returncode, r.stdout, r.stderr)
+
+
+def test_metadata_of_reference_written_files():
+    """usearch_metadata_buffer (U/c/lib.cpp:315-333) needs no device: metric / scalar kind / dimensions of the golden index
+    files written by the reference."""
+    from lantern_b200 import api
+    G = np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+    L = api.lib()
+    for name, metric, scalar, dims in (("cube_l2sq_file", 3, 1, 3), ("cube_cos_file", 1, 1, 3), ("lattice_f16_file", 3, 3, 3),
+                                       ("lattice_i8_file", 3, 4, 3), ("rand_cos_file", 1, 1, 12)):
+        buf = np.ascontiguousarray(G[name])
+        o = api.InitOptions()
+        err = C.c_char_p()
+        L.lb200_metadata_buffer(buf.ctypes.data, len(buf), C.byref(o), C.byref(err))
+        assert not err.value
+        assert (o.metric_kind, o.quantization, o.dimensions) == (metric, scalar, dims), name
+    err = C.c_char_p()
+    L.lb200_metadata_buffer(np.zeros(100, np.uint8).ctypes.data, 100, C.byref(api.InitOptions()), C.byref(err))
+    assert err.value and b"magic" in err.value
