@@ -338,6 +338,7 @@ struct ora_index {
     uint32_t* visit;
     uint32_t epoch;
     uint32_t rng; /* std::default_random_engine == minstd_rand0, default seed 1 */
+    int engine_order; /* 0 = the reference's heap; 1 = the CUDA engine's tie order (search only) */
     float *dec_a, *dec_b;
     uint8_t* cast_buf;
     ora_stats st;
@@ -404,6 +405,7 @@ int ora_reserve(ora_index* x, size_t cap) {
 }
 
 size_t ora_size(const ora_index* x) { return x->n; }
+void ora_set_engine_order(ora_index* x, int on) { x->engine_order = on; }
 size_t ora_dimensions(const ora_index* x) { return x->dims; }
 size_t ora_connectivity(const ora_index* x) { return x->M; }
 int ora_max_level(const ora_index* x) { return x->max_level; }
@@ -519,6 +521,66 @@ static void search_base(ora_index* x, const void* q, uint32_t start, size_t top_
             }
         }
     }
+}
+
+/* The same beam with the CUDA engine's queue discipline (lantern_b200/csrc/walk.cuh beam_impl): the candidate queue is the
+ * set of unexpanded entries of `top` (closest first; among equal distances the most recently inserted first, which is what
+ * insert-before-equal gives) plus a LIFO "limbo" of unexpanded entries evicted at exactly the current radius.  Identical to
+ * search_base whenever no two candidate distances are exactly equal; with ties only the ORDER of equal-distance expansions
+ * differs from the reference's binary heap.  Used to show that ties are the only source of id differences. */
+static void search_base_engine_order(ora_index* x, const void* q, uint32_t start, size_t top_limit) {
+    cvec_t* top = &x->top;
+    uint8_t* expanded = (uint8_t*)calloc(top_limit + 1, 1);
+    uint32_t limbo[64];
+    size_t limbo_n = 0, i;
+    float limbo_d = 0.f;
+    visits_clear(x);
+    top->n = 0;
+    cvec_reserve(top, top_limit + 1);
+    float radius = measure_qv(x, q, start);
+    top->e[0].d = radius, top->e[0].s = start, top->n = 1;
+    visits_set(x, start);
+    for (;;) {
+        uint32_t c = UINT32_MAX;
+        for (i = 0; i < top->n; ++i)
+            if (!expanded[i]) {
+                c = top->e[i].s, expanded[i] = 1;
+                break;
+            }
+        if (c == UINT32_MAX && limbo_n)
+            c = limbo[--limbo_n];
+        if (c == UINT32_MAX)
+            break;
+        x->st.base_pops++;
+        uint32_t n = x->cnt0[c], j;
+        const uint32_t* l = x->nbr0 + (size_t)c * x->M0;
+        for (j = 0; j < n; ++j) {
+            uint32_t s = l[j];
+            if (visits_set(x, s))
+                continue;
+            x->st.visited_members++;
+            float d = measure_qv(x, q, s);
+            if (top->n < top_limit || d < top->e[top->n - 1].d) {
+                size_t pos = sbuf_lower_bound(top, d), full = (top->n == top_limit);
+                float ev_d = 0.f;
+                uint32_t ev_s = UINT32_MAX;
+                int ev_expanded = 1;
+                if (full)
+                    ev_d = top->e[top_limit - 1].d, ev_s = top->e[top_limit - 1].s, ev_expanded = expanded[top_limit - 1];
+                size_t last = full ? top_limit - 1 : top->n;
+                memmove(top->e + pos + 1, top->e + pos, (last - pos) * sizeof(cand_t));
+                memmove(expanded + pos + 1, expanded + pos, last - pos);
+                top->e[pos].d = d, top->e[pos].s = s, expanded[pos] = 0;
+                top->n = last + 1;
+                radius = top->e[top->n - 1].d;
+                if (limbo_n && radius < limbo_d)
+                    limbo_n = 0;
+                if (ev_s != UINT32_MAX && !ev_expanded && ev_d == radius && limbo_n < 64)
+                    limbo[limbo_n++] = ev_s, limbo_d = radius;
+            }
+        }
+    }
+    free(expanded);
 }
 
 /* search_to_insert_, index.hpp:3324-3392. */
@@ -712,7 +774,10 @@ size_t ora_search(ora_index* x, const void* query, int kind, size_t k, size_t ef
     if (expansion < k)
         expansion = k;
     uint32_t closest = search_for_one(x, q, (uint32_t)x->entry, x->max_level, 0);
-    search_base(x, q, closest, expansion);
+    if (x->engine_order)
+        search_base_engine_order(x, q, closest, expansion);
+    else
+        search_base(x, q, closest, expansion);
     size_t found = x->top.n < k ? x->top.n : k, i;
     for (i = 0; i < found; ++i) {
         keys[i] = x->keys[x->top.e[i].s];

@@ -43,6 +43,7 @@ def lib():
             getattr(L, f).restype = C.c_size_t
             getattr(L, f).argtypes = [C.c_void_p]
         L.ora_max_level.argtypes = [C.c_void_p]
+        L.ora_set_engine_order.argtypes = [C.c_void_p, C.c_int]
         L.ora_entry_slot.restype = C.c_uint64
         L.ora_entry_slot.argtypes = [C.c_void_p]
         L.ora_add.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.POINTER(Stats)]
@@ -105,6 +106,9 @@ class PortIndex:
 
     def size(self):
         return lib().ora_size(self.h)
+
+    def set_engine_order(self, on=True):
+        lib().ora_set_engine_order(self.h, int(on))
 
     def add(self, key, vec, level=-1):
         vec = np.ascontiguousarray(vec)

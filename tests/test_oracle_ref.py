@@ -89,3 +89,25 @@ def test_pq_128_centroid_quirk(port, ref):
     assert np.allclose(mine, rd, rtol=1e-5, atol=1e-6)
     full = port.pq_compress(cb, X, nsub, compat128=False)
     assert (full >= 128).any()
+
+
+def test_engine_tie_order_mode_equals_reference_without_ties(port):
+    """The oracle's model of the CUDA engine's queue discipline is the reference's algorithm whenever distances are distinct
+    (ids AND work counters identical); with exact ties only equal-distance order may differ (same distance profile)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from util import build_port_index, structured
+    X, Q = structured(2500, 24, seed=3), structured(150, 24, seed=4)
+    p = build_port_index(port, X, "cos", "f32", M=12, efc=64, ef=40)
+    k1, d1, c1, t1 = p.search_batch(Q, 10)
+    p.set_engine_order(True)
+    k2, d2, c2, t2 = p.search_batch(Q, 10)
+    assert np.array_equal(k1, k2) and np.array_equal(d1, d2) and t1 == t2
+    rng = np.random.default_rng(9)
+    Xi = rng.integers(-3, 4, (2000, 12)).astype(np.float32)  # integer data: ties everywhere
+    Qi = rng.integers(-3, 4, (100, 12)).astype(np.float32)
+    p = build_port_index(port, Xi, "l2sq", "f32", M=8, efc=48, ef=24)
+    k1, d1, _, _ = p.search_batch(Qi, 10)
+    p.set_engine_order(True)
+    k2, d2, _, _ = p.search_batch(Qi, 10)
+    assert np.mean(d1 == d2) > 0.97
