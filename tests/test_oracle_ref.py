@@ -111,3 +111,29 @@ def test_engine_tie_order_mode_equals_reference_without_ties(port):
     p.set_engine_order(True)
     k2, d2, _, _ = p.search_batch(Qi, 10)
     assert np.mean(d1 == d2) > 0.97
+
+
+def test_property_port_equals_reference_on_random_small_configs(port, ref):
+    """Property test (hypothesis): for random (N, d, M, ef_construction, ef, metric) and integer-valued data the
+    restatement and the compiled reference write the same index file and return the same ids and distances."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=20, deadline=None)
+    @given(n=st.integers(2, 300), d=st.integers(1, 20), M=st.sampled_from([2, 3, 4, 8, 16]), efc=st.integers(4, 64),
+           ef=st.integers(1, 48), metric=st.sampled_from(["l2sq", "cos"]), seed=st.integers(0, 10_000))
+    def check(n, d, M, efc, ef, metric, seed):
+        rng = np.random.default_rng(seed)
+        X = rng.integers(-5, 6, (n, d)).astype(np.float32)
+        r = ref.RefIndex(d, metric, M=M, efc=efc, ef=ef)
+        p = port.PortIndex(d, metric, M=M, efc=efc, ef=ef)
+        r.reserve(n), p.reserve(n)
+        for i in range(n):
+            r.add(i + 1, X[i]), p.add(i + 1, X[i])
+        assert np.array_equal(trim(r.save_buffer()), p.save_buffer())
+        for q in rng.integers(-5, 6, (10, d)).astype(np.float32):
+            k = int(rng.integers(1, 12))
+            rk, rd = r.search(q, k)
+            pk, pd, _ = p.search(q, k)
+            assert np.array_equal(rk, pk) and np.array_equal(rd, pd)
+
+    check()
