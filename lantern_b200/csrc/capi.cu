@@ -294,6 +294,8 @@ LB200_EXPORT void lb200_search_batch_device(lb200_index_t h, void const* d_queri
 
 LB200_EXPORT void lb200_last_search_stats(lb200_index_t h, lb200_search_stats_t* stats, lb200_error_t* error) {
     guarded(error, [&] {
+        if (!stats)
+            throw CudaError("null stats pointer");
         SearchStats s = as_index(h)->last_stats();
         stats->queries = s.queries;
         stats->computed_distances = s.computed_distances;

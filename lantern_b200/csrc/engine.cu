@@ -192,6 +192,7 @@ void Index::add_host(const uint64_t* keys, const void* vectors, size_t n, size_t
     if (!n)
         return;
     check_input_kind(cfg_, kind);
+    std::lock_guard<std::recursive_mutex> hg(host_mu_);
     const size_t in_bytes = scalar_row_bytes(kind, cfg_.dims);
     void* d_tmp = nullptr;
     {
@@ -342,6 +343,7 @@ void Index::search_host(const void* queries, size_t nq, size_t stride, int kind,
     if (!nq || !k)
         return;
     check_input_kind(cfg_, kind);
+    std::lock_guard<std::recursive_mutex> hg(host_mu_); // the staging buffer is shared by every host-buffer call of this index
     flush_staged(); // before the io buffer holds the queries: flushing stages rows through the same buffer
     const size_t in_bytes = scalar_row_bytes(kind, cfg_.dims);
     uint8_t* base = nullptr;

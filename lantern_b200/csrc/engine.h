@@ -154,6 +154,7 @@ class Index {
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     uint32_t last_nq_ = 0;
     std::mutex mu_;
+    std::recursive_mutex host_mu_; // whole host-buffer calls (they share d_io_buf_); always taken before mu_
     // streaming state of the single-query entry point (usearch_search_ef continue_search, scan.c:240-292)
     std::vector<uint8_t> stream_query_;
     std::vector<uint64_t> stream_returned_; // keys handed out so far for stream_query_
