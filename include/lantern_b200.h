@@ -125,6 +125,8 @@ LB200_EXPORT size_t lb200_connectivity(lb200_index_t, lb200_error_t* error);
 LB200_EXPORT size_t lb200_expansion_add(lb200_index_t, lb200_error_t* error);
 LB200_EXPORT size_t lb200_expansion_search(lb200_index_t, lb200_error_t* error);
 LB200_EXPORT lb200_index_metadata_t lb200_index_metadata(lb200_index_t, lb200_error_t* error);
+LB200_EXPORT size_t lb200_count(lb200_index_t, lb200_key_t key, lb200_error_t* error);  /* usearch.h:263 */
+LB200_EXPORT bool lb200_contains(lb200_index_t, lb200_key_t key, lb200_error_t* error); /* usearch.h:255 */
 
 /* ---- build path: usearch.h:236-247; batch forms are new ---------------------------------------- */
 LB200_EXPORT void lb200_reserve(lb200_index_t, size_t capacity, lb200_error_t* error);
@@ -184,6 +186,9 @@ LB200_EXPORT void lb200_load(lb200_index_t, char const* path, lb200_error_t* err
 LB200_EXPORT void lb200_view(lb200_index_t, char const* path, lb200_error_t* error);
 LB200_EXPORT void lb200_metadata_buffer(void const* buffer, size_t length, lb200_init_options_t* options,
                                         lb200_error_t* error);
+LB200_EXPORT void lb200_metadata(char const* path, lb200_init_options_t* options, lb200_error_t* error); /* usearch.h:186 */
+/* usearch.h:175 -- writes the first 136 bytes of a save (head, header, vector_size_bytes, node_count) to `headerp` */
+LB200_EXPORT void lb200_update_header(lb200_index_t, char* headerp, lb200_error_t* error);
 LB200_EXPORT uint64_t lb200_header_get_entry_slot(char* headerp);               /* lib.cpp:219-225 */
 LB200_EXPORT void lb200_header_set_entry_slot(char* headerp, uint64_t entry_slot); /* lib.cpp:227-231 */
 
@@ -245,6 +250,20 @@ LB200_EXPORT int lb200_device_count(void);
 LB200_EXPORT char const* lb200_version(void);
 /* number of engine kernels launched by this process so far (bench.py's gpu_launches) */
 LB200_EXPORT uint64_t lb200_kernel_launches(void);
+
+/* ---- the rest of U/c/usearch.h, exported under the reference names only so that binaries built against usearch.h link:
+ * the in-Postgres page storage (nodes fetched from caller memory through retriever callbacks) and label bookkeeping.
+ * Each sets *error to a static string that says what to call instead and returns 0; none touches the device. ---------- */
+LB200_EXPORT void usearch_view_mem_lazy(lb200_index_t, char* data, lb200_error_t* error);                     /* :174 */
+LB200_EXPORT void usearch_set_node_retriever(lb200_index_t, void* retriever_ctx, lb200_node_retriever_t retriever,
+                                             lb200_node_retriever_t retriever_mut, lb200_error_t* error);     /* :352 */
+LB200_EXPORT void usearch_add_external(lb200_index_t, lb200_key_t key, void const* vector, void* tape,
+                                       lb200_scalar_kind_t kind, int16_t level, uint64_t slot, lb200_error_t* error); /* :355 */
+LB200_EXPORT int32_t usearch_newnode_level(lb200_index_t, lb200_error_t* error);                              /* :347 */
+LB200_EXPORT size_t usearch_get(lb200_index_t, lb200_key_t key, size_t count, void* vector, lb200_scalar_kind_t kind,
+                                lb200_error_t* error);                                                        /* :307 */
+LB200_EXPORT size_t usearch_remove(lb200_index_t, lb200_key_t key, lb200_error_t* error);                     /* :317 */
+LB200_EXPORT size_t usearch_rename(lb200_index_t, lb200_key_t from, lb200_key_t to, lb200_error_t* error);    /* :326 */
 
 #ifdef __cplusplus
 }

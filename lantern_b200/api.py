@@ -92,6 +92,10 @@ SIGNATURES = {
     "lb200_load": (None, [C.c_void_p, C.c_char_p, ERRP]),
     "lb200_view": (None, [C.c_void_p, C.c_char_p, ERRP]),
     "lb200_metadata_buffer": (None, [C.c_void_p, C.c_size_t, C.POINTER(InitOptions), ERRP]),
+    "lb200_metadata": (None, [C.c_char_p, C.POINTER(InitOptions), ERRP]),
+    "lb200_update_header": (None, [C.c_void_p, C.c_void_p, ERRP]),
+    "lb200_count": (C.c_size_t, [C.c_void_p, C.c_uint64, ERRP]),
+    "lb200_contains": (C.c_bool, [C.c_void_p, C.c_uint64, ERRP]),
     "lb200_header_get_entry_slot": (C.c_uint64, [C.c_void_p]),
     "lb200_header_set_entry_slot": (None, [C.c_void_p, C.c_uint64]),
     "lb200_distance": (C.c_float, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, ERRP]),

@@ -387,6 +387,42 @@ LB200_EXPORT void lb200_metadata_buffer(void const* buffer, size_t length, lb200
     });
 }
 
+LB200_EXPORT void lb200_metadata(char const* path, lb200_init_options_t* options, lb200_error_t* error) {
+    guarded(error, [&] { // U/c/lib.cpp:268-284: only the 80-byte dense head is read
+        if (!path || !options)
+            throw CudaError("null path or options");
+        FILE* f = fopen(path, "rb");
+        if (!f)
+            throw CudaError("Can't open file for reading");
+        uint8_t head[80];
+        const size_t r = fread(head, 1, sizeof(head), f);
+        fclose(f);
+        if (r != sizeof(head))
+            throw CudaError("index file: truncated head");
+        lb200_error_t inner = nullptr;
+        lb200_metadata_buffer(head, sizeof(head), options, &inner);
+        if (inner)
+            throw CudaError(inner);
+    });
+}
+
+LB200_EXPORT void lb200_update_header(lb200_index_t h, char* headerp, lb200_error_t* error) {
+    guarded(error, [&] {
+        if (!headerp)
+            throw CudaError("null header buffer");
+        as_index(h)->write_header(headerp);
+    });
+}
+
+LB200_EXPORT size_t lb200_count(lb200_index_t h, lb200_key_t key, lb200_error_t* error) {
+    size_t r = 0;
+    guarded(error, [&] { r = as_index(h)->count_key(key); });
+    return r;
+}
+LB200_EXPORT bool lb200_contains(lb200_index_t h, lb200_key_t key, lb200_error_t* error) {
+    return lb200_count(h, key, error) != 0;
+}
+
 LB200_EXPORT uint64_t lb200_header_get_entry_slot(char* headerp) {
     uint64_t res = 0;
     memcpy(&res, headerp + 80 + 32, 6);
@@ -644,6 +680,47 @@ LB_ALIAS(void, usearch_exact_search, lb200_exact_search,
 LB_ALIAS(void, usearch_cast, lb200_cast,
          (lb200_scalar_kind_t f, void const* v, lb200_scalar_kind_t t, void* r, size_t rs, int d, lb200_error_t* e),
          (f, v, t, r, rs, d, e))
+LB_ALIAS(void, usearch_metadata, lb200_metadata, (char const* p, lb200_init_options_t* o, lb200_error_t* e), (p, o, e))
+LB_ALIAS(void, usearch_update_header, lb200_update_header, (lb200_index_t h, char* hp, lb200_error_t* e), (h, hp, e))
+LB_ALIAS(size_t, usearch_count, lb200_count, (lb200_index_t h, lb200_key_t k, lb200_error_t* e), (h, k, e))
+LB_ALIAS(bool, usearch_contains, lb200_contains, (lb200_index_t h, lb200_key_t k, lb200_error_t* e), (h, k, e))
 #undef LB_ALIAS
+
+// ---- the rest of U/c/usearch.h: entry points of the reference's in-Postgres page storage and of label bookkeeping.  They are
+// exported so that a binary built against usearch.h links unchanged; each reports, through the usual error convention, why it
+// cannot work on a graph that lives in HBM and what to call instead. -----------------------------------------
+static void unsupported(lb200_error_t* error, const char* msg) {
+    if (error)
+        *error = msg;
+}
+LB200_EXPORT void usearch_view_mem_lazy(lb200_index_t, char*, lb200_error_t* error) { // usearch.h:174
+    unsupported(error, "usearch_view_mem_lazy: nodes cannot be fetched lazily from caller memory into HBM; pass the whole "
+                       "index file to usearch_load_buffer");
+}
+LB200_EXPORT void usearch_set_node_retriever(lb200_index_t, void*, lb200_node_retriever_t, lb200_node_retriever_t,
+                                             lb200_error_t* error) { // usearch.h:352-353
+    unsupported(error, "usearch_set_node_retriever: external node retrievers are not supported; load the index with "
+                       "usearch_load_buffer");
+}
+LB200_EXPORT void usearch_add_external(lb200_index_t, lb200_key_t, void const*, void*, lb200_scalar_kind_t, int16_t, uint64_t,
+                                       lb200_error_t* error) { // usearch.h:355-357
+    unsupported(error, "usearch_add_external: node tapes live in HBM, not in caller pages; use usearch_add / lb200_add_batch");
+}
+LB200_EXPORT int32_t usearch_newnode_level(lb200_index_t, lb200_error_t* error) { // usearch.h:347
+    unsupported(error, "usearch_newnode_level: levels are drawn inside lb200_build (same generator as the reference)");
+    return 0;
+}
+LB200_EXPORT size_t usearch_get(lb200_index_t, lb200_key_t, size_t, void*, lb200_scalar_kind_t, lb200_error_t* error) { // :307
+    unsupported(error, "usearch_get: not supported (Lantern never calls it); read vectors back with usearch_save_buffer");
+    return 0;
+}
+LB200_EXPORT size_t usearch_remove(lb200_index_t, lb200_key_t, lb200_error_t* error) { // usearch.h:317
+    unsupported(error, "usearch_remove: not supported; Lantern marks deletions with label 0 and filters them in scan.c:294-300");
+    return 0;
+}
+LB200_EXPORT size_t usearch_rename(lb200_index_t, lb200_key_t, lb200_key_t, lb200_error_t* error) { // usearch.h:326
+    unsupported(error, "usearch_rename: not supported");
+    return 0;
+}
 
 } // extern "C"

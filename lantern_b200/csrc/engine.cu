@@ -240,6 +240,17 @@ void Index::flush_staged() {
     add_host(keys.data(), rows.data(), keys.size(), scalar_row_bytes(kind, cfg_.dims), kind);
 }
 
+// usearch_count / usearch_contains (U/c/lib.cpp:392-400): keys live in a host mirror, no device work
+size_t Index::count_key(uint64_t key) {
+    size_t c = 0;
+    {
+        std::lock_guard<std::mutex> g(stage_mu_);
+        c += (size_t)std::count(staged_keys_.begin(), staged_keys_.end(), key);
+    }
+    std::lock_guard<std::mutex> g(mu_);
+    return c + (size_t)std::count(h_keys_.begin(), h_keys_.end(), key);
+}
+
 void Index::build() {
     flush_staged();
     std::lock_guard<std::mutex> g(mu_);

@@ -97,6 +97,9 @@ class Index {
     size_t serialized_length();
     size_t save_buffer(void* buffer, size_t length);
     void load_buffer(const void* buffer, size_t length);
+    void write_header(void* headerp);      // 136 bytes (usearch_update_header)
+    void fill_header(uint8_t* p) const;    // caller holds mu_
+    size_t count_key(uint64_t key);        // usearch_count: vectors stored under `key`
 
     GraphView view() const;
 

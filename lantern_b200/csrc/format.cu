@@ -85,6 +85,32 @@ size_t Index::serialized_length() {
     return total;
 }
 
+// The 136 bytes in front of the node tapes: dense head, serialized header, vector_size_bytes, node_count.  Caller holds mu_.
+void Index::fill_header(uint8_t* p) const {
+    memset(p, 0, 80);
+    memcpy(p, "usearch", 7);
+    const uint16_t ver[3] = {2, 8, 14};
+    memcpy(p + 7, ver, 6);
+    p[13] = metric_char(cfg_.metric_kind), p[14] = scalar_code(cfg_.scalar_kind), p[15] = 8, p[16] = 16;
+    uint64_t v = n_;
+    memcpy(p + 17, &v, 8);
+    v = 0;
+    memcpy(p + 25, &v, 8);
+    v = cfg_.dims;
+    memcpy(p + 33, &v, 8);
+    const uint64_t hdr[7] = {n_, cfg_.M, cfg_.M0, (uint64_t)(max_level_ < 0 ? 0 : max_level_), entry_, vec_bytes_, n_};
+    memcpy(p + 80, hdr, 56);
+}
+
+// usearch_update_header (U/c/lib.cpp:213-217 -> index_dense.hpp:962-965): the first 136 bytes of a save.
+void Index::write_header(void* headerp) {
+    flush_staged();
+    std::lock_guard<std::mutex> g(mu_);
+    if (pending_n_)
+        build_pending(*this);
+    fill_header((uint8_t*)headerp);
+}
+
 size_t Index::save_buffer(void* buffer, size_t length) {
     const size_t need = serialized_length();
     std::lock_guard<std::mutex> g(mu_);
@@ -102,21 +128,8 @@ size_t Index::save_buffer(void* buffer, size_t length) {
         LB_CUDA(cudaMemcpy(rows.data(), d_vectors_, rows.size(), cudaMemcpyDeviceToHost));
     }
     uint8_t* p = (uint8_t*)buffer;
-    memset(p, 0, 80);
-    memcpy(p, "usearch", 7);
-    const uint16_t ver[3] = {2, 8, 14};
-    memcpy(p + 7, ver, 6);
-    p[13] = metric_char(cfg_.metric_kind), p[14] = scalar_code(cfg_.scalar_kind), p[15] = 8, p[16] = 16;
-    uint64_t v = n_;
-    memcpy(p + 17, &v, 8);
-    v = 0;
-    memcpy(p + 25, &v, 8);
-    v = cfg_.dims;
-    memcpy(p + 33, &v, 8);
-    p += 80;
-    const uint64_t hdr[7] = {n_, M, M0, (uint64_t)(max_level_ < 0 ? 0 : max_level_), entry_, vec_bytes_, n_};
-    memcpy(p, hdr, 56);
-    p += 56;
+    fill_header(p);
+    p += 136;
     for (size_t i = 0; i < n_; ++i) {
         memcpy(p, &h_keys_[i], 8);
         memcpy(p + 8, &h_levels_[i], 2);

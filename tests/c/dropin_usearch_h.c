@@ -51,6 +51,16 @@ int main(void) {
     usearch_save_buffer(idx, buf, len, &error);
     if (error || memcmp(buf, "usearch", 7) != 0 || usearch_header_get_entry_slot(buf) >= 8)
         return 1;
+    char header[136]; /* insert.c persists this into the index header page after every insert */
+    usearch_update_header(idx, header, &error);
+    if (error || memcmp(header, buf, sizeof(header)) != 0)
+        return 1;
+    if (usearch_count(idx, 102, &error) != 1 || usearch_contains(idx, 5, &error) || error)
+        return 1;
+    usearch_view_mem_lazy(idx, header, &error); /* page storage: must refuse, not crash */
+    if (!error)
+        return 1;
+    error = NULL;
     usearch_index_metadata_t meta = usearch_index_metadata(idx, &error);
     if (meta.neighbors_bytes != 16 || meta.neighbors_base_bytes != 28) /* 4+6M / 4+12M for M=2 */
         return 1;

@@ -165,3 +165,77 @@ def test_metadata_of_reference_written_files():
     err = C.c_char_p()
     L.lb200_metadata_buffer(np.zeros(100, np.uint8).ctypes.data, 100, C.byref(api.InitOptions()), C.byref(err))
     assert err.value and b"magic" in err.value
+
+
+def test_metadata_from_path(tmp_path):
+    """usearch_metadata (U/c/lib.cpp:268-284): the same answer from a file on disk; errors through the usual convention."""
+    from lantern_b200 import api
+    G = np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+    L = api.lib()
+    path = tmp_path / "lattice_f16.usearch"
+    path.write_bytes(bytes(np.ascontiguousarray(G["lattice_f16_file"])))
+    for fn in (L.lb200_metadata, L.usearch_metadata):
+        fn.restype, fn.argtypes = None, [C.c_char_p, C.POINTER(api.InitOptions), C.POINTER(C.c_char_p)]
+        o, err = api.InitOptions(), C.c_char_p()
+        fn(str(path).encode(), C.byref(o), C.byref(err))
+        assert not err.value
+        assert (o.metric_kind, o.quantization, o.dimensions, o.connectivity) == (3, 3, 3, 0)
+        err = C.c_char_p()
+        fn(str(tmp_path / "missing").encode(), C.byref(api.InitOptions()), C.byref(err))
+        assert err.value and b"open" in err.value
+    short = tmp_path / "short"
+    short.write_bytes(b"usearch")
+    err = C.c_char_p()
+    L.lb200_metadata(str(short).encode(), C.byref(api.InitOptions()), C.byref(err))
+    assert err.value and b"truncated" in err.value
+
+
+def reference_header_symbols():
+    path = "/root/reference/lantern_hnsw/third_party/usearch/c/usearch.h"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present")
+    names = set(re.findall(r"\b(usearch_[a-z0-9_]+)\s*\(", open(path).read()))
+    return sorted(n for n in names if not n.endswith("_t"))  # `usearch_distance_t (*usearch_metric_t)(...)` is a typedef
+
+
+def test_every_entry_point_of_the_reference_header_is_exported():
+    """A binary built against U/c/usearch.h must link against this library unchanged."""
+    from lantern_b200 import api
+    L = api.lib()
+    names = reference_header_symbols()
+    assert len(names) >= 35
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_page_storage_entry_points_explain_themselves():
+    """The reference's in-Postgres page storage / label bookkeeping entry points are exported but cannot work on a graph in
+    HBM: they must say so through usearch_error_t (never crash, never pretend), with or without a device."""
+    from lantern_b200 import api
+    L = api.lib()
+    P = C.POINTER(C.c_char_p)
+    calls = {
+        "usearch_view_mem_lazy": ([C.c_void_p, C.c_void_p, P], (None, None)),
+        "usearch_set_node_retriever": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, P], (None, None, None, None)),
+        "usearch_add_external": ([C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_int16, C.c_uint64, P],
+                                 (None, 1, None, None, 1, 0, 0)),
+        "usearch_newnode_level": ([C.c_void_p, P], (None,)),
+        "usearch_get": ([C.c_void_p, C.c_uint64, C.c_size_t, C.c_void_p, C.c_int, P], (None, 1, 1, None, 1)),
+        "usearch_remove": ([C.c_void_p, C.c_uint64, P], (None, 1)),
+        "usearch_rename": ([C.c_void_p, C.c_uint64, C.c_uint64, P], (None, 1, 2)),
+    }
+    for name, (argtypes, args) in calls.items():
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = None if name in ("usearch_view_mem_lazy", "usearch_set_node_retriever", "usearch_add_external") else C.c_size_t
+        err = C.c_char_p()
+        r = fn(*args, C.byref(err))
+        assert err.value and name.encode() in err.value, name
+        assert not r
+    # and the ones that need an index report a null handle instead of dereferencing it
+    for name, args in (("lb200_count", (None, 5)), ("lb200_update_header", (None, None))):
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = api.SIGNATURES[name]
+        err = C.c_char_p()
+        fn(*args, C.byref(err))
+        assert err.value and b"null" in err.value
