@@ -1,11 +1,13 @@
 #!/usr/bin/env python
 """bench.py -- batched HNSW search throughput of the B200 engine (and of the reference on the host cores).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg2s]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg4|cfg5s|...]
 
 One "step" = one batch of queries through the hot path (greedy descent + ef-wide base-layer beam + top-k) over a
-synthetic corpus resident in HBM.  Workload (BASELINE.json configs[1], "cfg2"): 1 M x d768 fp32, structured synthetic
-(x = z P + 0.05 eps, 32-d latent), l2sq, M=16, ef_construction=128, ef=64, batch 1024, k=10, 1 x B200.
+synthetic corpus resident in HBM.  Default workload = the configuration BASELINE.json's metric is quoted on ("d=768 fp32,
+10M vectors, batch 4096", configs[2], "cfg3"; 30.7 GB, fits one B200): 10 M x d768 fp32, structured synthetic
+(x = z P + 0.05 eps, 32-d latent), cosine, M=32, ef_construction=128, ef=128, batch 4096, k=10, on
+1/2/4/8 GPUs (row-range shards).  `--workload cfg2` = configs[1] (1 M, l2sq, M=16, ef=64, batch 1024), and so on.
 The graph is built by the engine itself on the GPU (lb200_add_batch_device + lb200_build) before the timed region.
 
 `value`  : queries/s, queries already resident in HBM (lb200_search_batch_device), CUDA events on the launching stream.
@@ -16,10 +18,12 @@ The graph is built by the engine itself on the GPU (lb200_add_batch_device + lb2
            against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
 `cpu_baseline`: the UNMODIFIED reference (oracle/_ref, usearch compiled from /root/reference) on all host cores,
            loading the very index file the engine wrote (usearch file format) and searching the same queries --
-           which also yields the full-size same-graph id parity reported under `parity`.
---impl reference: the reference alone on the host cores: builds its own graph over a bounded prefix of the corpus
-           (sized for ~1 minute of multi-threaded adds) and searches the same query batches.
-Steps cycle through a pool of distinct query batches; the corpus (3 GB), gathered at random, is far larger than L2 (126 MB).
+           which also yields the same-graph id parity reported under `parity`.  Corpora above 8 GB (cfg3): the engine
+           builds a second graph over the first --cpu-prefix-rows rows for this purpose (bounded sample).
+--impl reference: the reference alone on the host cores: builds its own graph over a bounded number of rows of the
+           corpus generator (sized for ~1 minute of multi-threaded adds) and searches the same query batches.
+Steps cycle through a pool of distinct query batches; the corpus (30.7 GB; 3 GB for cfg2), gathered at random, is far
+larger than L2 (126 MB).
 """
 import argparse
 import json
@@ -41,7 +45,9 @@ WORKLOADS = {
                  desc="cfg2: 1M x d768 f32 l2sq, M=16 efc=128 ef=64, batch-1024 k=10"),
     "cfg2s": dict(n=100_000, dim=768, metric="l2sq", M=16, efc=128, ef=64, batch=1024, k=10,
                   desc="cfg2s (smoke-size): 100k x d768 f32 l2sq, M=16 efc=128 ef=64, batch-1024 k=10"),
-    "cfg3": dict(n=10_000_000, dim=768, metric="cos", M=32, efc=128, ef=128, batch=4096, k=10,
+    # recall_1gpu: recall@10 of the unsharded graph at this ef as measured by the 1-GPU run of this very bench
+    # (profiles/r01_bench_cfg3_10M_cos.json); the sharded runs match it when --recall-target is not given
+    "cfg3": dict(n=10_000_000, dim=768, metric="cos", M=32, efc=128, ef=128, batch=4096, k=10, recall_1gpu=0.88125,
                  desc="cfg3: 10M x d768 f32 cosine, M=32 efc=128 ef=128, batch-4096 k=10"),
     "cfg4": dict(n=10_000_000, dim=1536, metric="l2sq", M=16, efc=128, ef=64, batch=4096, k=100, pq=(96, 256),
                  desc="cfg4: 10M x d1536 f32 -> PQ 96 subvectors x 256 centroids, l2sq, M=16 efc=128 ef=64 (expansion 100), batch-4096 k=100"),
@@ -57,6 +63,8 @@ WORKLOADS = {
 }
 METRIC_NAME = "queries/sec @ recall@10, d=768 fp32, 10M vectors, batch 4096, 1/2/4/8 B200"
 LATENT, NOISE = 32, 0.05
+BIG_CORPUS_BYTES = 8e9  # above this the index file is not handed to the reference whole (cpu_baseline) nor rebuilt unsharded per rank
+DEVICE_TYPE, DIST_BACKEND = "cuda", "nccl"  # tests/test_bench_dryrun.py walks run_ours on the CPU with a stand-in engine
 SEED_P, SEED_CORPUS, SEED_QUERY = 1234, 42, 43
 
 
@@ -193,27 +201,36 @@ def run_reference(args, wl):
     # the rate is measured on a pilot of 20k rows (it only falls slowly, ~log N, afterwards)
     pilot = min(wl["n"], 20_000)
     gen = bits_np if wl.get("kind") == "b1" else structured_np
-    X = gen(wl["n"] if args.ref_rows == 0 else min(wl["n"], args.ref_rows), wl["dim"], SEED_CORPUS)
     nsteps = args.steps + args.warmup
     pool = min(nsteps, args.query_pool)
     Q = gen(pool * wl["batch"], wl["dim"], SEED_QUERY)
+    # rows are drawn from the corpus generator as they are needed (the reference never sees more than the prefix it can index
+    # in its build budget, so the 30 GB of cfg3 are not materialised): the pilot first, the rest once its size is known
+    Xp = gen(pilot if args.ref_rows == 0 else min(wl["n"], args.ref_rows), wl["dim"], SEED_CORPUS)
     pqkw = {}
     if wl.get("pq"):  # codebook for the reference arm: 256 corpus rows (a valid, if untrained, codebook), stated in `sample`
         nsub, ncent = wl["pq"]
         pqkw = dict(pq=True, num_centroids=ncent, num_subvectors=nsub,
-                    codebook=X[np.random.default_rng(7).choice(len(X), ncent, replace=False)].copy())
+                    codebook=Xp[np.random.default_rng(7).choice(len(Xp), ncent, replace=False)].copy())
     idx = reflib.RefIndex(wl["dim"], wl["metric"], wl.get("kind", "f32"), M=wl["M"], efc=wl["efc"], ef=wl["ef"], threads=cores, **pqkw)
-    idx.reserve(len(X))
-    keys = np.arange(1, len(X) + 1, dtype=np.uint64)
+    pilot = min(pilot, len(Xp))
+    idx.reserve(len(Xp))
     t0 = time.perf_counter()
-    idx.add_batch(keys[:pilot], X[:pilot], threads=cores)
+    idx.add_batch(np.arange(1, pilot + 1, dtype=np.uint64), Xp[:pilot], threads=cores)
     t_pilot = time.perf_counter() - t0
-    n_ref = len(X)
+    t_build = t_pilot
+    n_ref = len(Xp)
     if not args.ref_rows:
-        n_ref = int(min(len(X), max(pilot, 0.7 * (pilot / t_pilot) * args.ref_build_seconds)))
+        n_ref = int(min(wl["n"], max(pilot, 0.7 * (pilot / t_pilot) * args.ref_build_seconds)))
+        Xr = gen(n_ref - pilot, wl["dim"], SEED_CORPUS + 7919) if n_ref > pilot else Xp[:0]
+        idx.reserve(n_ref)  # grows the pilot's reservation (per-thread visited sets scale with it: reserve what is used)
+    else:
+        Xr = Xp[pilot:]
     if n_ref > pilot:
-        idx.add_batch(keys[pilot:n_ref], X[pilot:n_ref], threads=cores)
-    t_build = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        idx.add_batch(np.arange(pilot + 1, n_ref + 1, dtype=np.uint64), Xr, threads=cores)
+        t_build += time.perf_counter() - t0
+    del Xp, Xr
     # each timed step is a bounded sample of the batch, sized from the warm-up rate so that K steps take about a minute
     B = wl["batch"]
     t0 = time.perf_counter()
@@ -229,8 +246,8 @@ def run_reference(args, wl):
         times.append(time.perf_counter() - t0)
     total = sum(times)
     value = args.steps * per_step / total
-    sample = ("reference builds its own graph over the first %d of %d corpus rows (%.0f s, %d threads); each step = the first %d "
-              "queries of a %d-query batch" % (n_ref, wl["n"], t_build, cores, per_step, B))
+    sample = ("reference builds its own graph over %d rows drawn from the %d-row corpus generator (%.0f s, %d threads); each step = "
+              "the first %d queries of a %d-query batch" % (n_ref, wl["n"], t_build, cores, per_step, B))
     line = {
         "impl": "reference", "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -289,9 +306,9 @@ def run_ours(args, wl):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group(DIST_BACKEND, device_id=torch.device(DEVICE_TYPE, local) if DEVICE_TYPE == "cuda" else None)
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    dev = torch.device(DEVICE_TYPE, local if DEVICE_TYPE == "cuda" else 0)
     api.lib()
 
     n, dim, k, ef, B = wl["n"], wl["dim"], wl["k"], wl["ef"], wl["batch"]
@@ -427,7 +444,7 @@ def run_ours(args, wl):
         target = torch.zeros(1, dtype=torch.float64, device=dev)
         full = None
         build_full = args.recall_target <= 0 and args.shard_ef >= 0 or args.replicated_comparison
-        if build_full and n * rowb <= 8e9:
+        if build_full and n * rowb <= BIG_CORPUS_BYTES:
             Xfull = gen_t(n, dim, SEED_CORPUS, dev)
             full = api.Index(dim, wl["metric"], kind, M=wl["M"], efc=wl["efc"], ef=ef)
             full.reserve(n)
@@ -440,8 +457,13 @@ def run_ours(args, wl):
             torch.cuda.synchronize()
             if rank == 0:
                 target[0] = recall_at_k(fk[:nrec].cpu().numpy(), truth)
+        target_src = "unsharded graph built and searched in this run (rank 0)"
         if args.recall_target > 0:
             target[0] = args.recall_target
+            target_src = "--recall-target"
+        elif full is None and args.shard_ef == 0 and wl.get("recall_1gpu"):
+            target[0] = wl["recall_1gpu"]
+            target_src = "recorded 1-GPU run of this bench (WORKLOADS[...]['recall_1gpu']); corpus too large to rebuild unsharded per rank"
         dist.broadcast(target, 0)
         target = float(target.item())
         sweep = {}
@@ -462,7 +484,8 @@ def run_ours(args, wl):
             chosen = ef  # "same-ef" mode
         state["ef"] = chosen
         ef_shard = chosen
-        shard_info = {"recall_target_unsharded_1gpu": target, "sweep_merged_recall_by_ef": sweep, "ef_per_shard": chosen}
+        shard_info = {"recall_target_unsharded_1gpu": target, "recall_target_source": target_src,
+                      "sweep_merged_recall_by_ef": sweep, "ef_per_shard": chosen}
         def timed(fn, reps):
             for s_ in range(3):
                 fn(s_)
@@ -641,47 +664,75 @@ def run_ours(args, wl):
                             "sample": "unmodified usearch (oracle/_ref) builds its own pq graph over the first %d of %d rows (%.0f s) "
                                       "with the same codebook and searches %d queries (%.1f s) on %d threads" % (
                                           n_ref, n, t_rb, done, spent, cores)}
-    if world == 1 and not args.no_cpu_baseline and not pq and n * rowb <= 8e9:  # the reference needs the index file twice in host RAM
+    cpu_note = None
+    if world == 1 and not args.no_cpu_baseline and not pq:
         from oracle import reflib
         if reflib.available():
-            cores = reflib.lib().refx_hardware_threads()
-            t0 = time.perf_counter()
-            buf = idx.save_buffer()
-            ridx = reflib.RefIndex(dim, wl["metric"], kind, M=wl["M"], efc=wl["efc"], ef=ef, threads=cores)
-            ridx.load_buffer(buf)
-            t_load = time.perf_counter() - t0
-            del buf
-            ridx._loaded = None
-            qh = Q.cpu().numpy()
-            spent, done, first = 0.0, 0, None
-            s = 0
-            while spent < args.cpu_seconds and s < pool:
-                qb = qh[s * B:(s + 1) * B]
+            b_idx = idx
+            try:
+                cores = reflib.lib().refx_hardware_threads()
+                b_n, b_truth, b_what = n, truth, "the engine's %d-node index file" % n
+                if n * rowb > BIG_CORPUS_BYTES:
+                    # The reference needs the index file twice in host RAM (35 GB each for cfg3) and half a minute to parse it:
+                    # bounded sample instead.  The engine builds a second graph, same parameters, over the first
+                    # --cpu-prefix-rows corpus rows; the reference loads THAT file and answers the same query batches.
+                    b_n = min(n, args.cpu_prefix_rows)
+                    b_idx = api.Index(dim, wl["metric"], kind, M=wl["M"], efc=wl["efc"], ef=ef)
+                    b_idx.reserve(b_n)
+                    b_idx.add_batch_device(np.arange(1, b_n + 1, dtype=np.uint64), X.data_ptr(), b_n, rowb, kind)
+                    b_idx.build()
+                    btk = torch.empty((nrec, k), dtype=torch.int64, device=dev)
+                    btd = torch.empty((nrec, k), dtype=torch.float32, device=dev)
+                    api.exact_search_device(X.data_ptr(), b_n, rowb, Q.data_ptr(), nrec, rowb, k, btk.data_ptr(), btd.data_ptr(),
+                                            wl["metric"], kind, dim, stream.cuda_stream)
+                    btk += 1  # offsets -> keys
+                    torch.cuda.synchronize()
+                    b_truth = btk.cpu().numpy()
+                    b_what = ("the index file the engine built over the first %d of the %d corpus rows (same M/efc/ef; the full file "
+                              "would not fit twice in host RAM next to the corpus)" % (b_n, n))
                 t0 = time.perf_counter()
-                rkeys, rd, rc, comp, vis = ridx.search_batch(qb, k, threads=cores)
-                spent += time.perf_counter() - t0
-                done += B
-                if first is None:
-                    first = (rkeys, rd, comp)
-                s += 1
-            cpu_qps = done / spent
-            cpu_baseline = {"value": cpu_qps, "unit": "queries/s", "cores": cores, "kind": "reference",
-                            "sample": "unmodified usearch (oracle/_ref) loads the engine's %d-node index file (%.0f s) and searches "
-                                      "%d of the bench's query batches (%d queries, %.1f s) on %d threads" % (
-                                          n, t_load, s, done, spent, cores)}
-            # same-graph parity at full size: step-0 queries, ids position-wise
-            idx.search_batch_device(Q.data_ptr(), B, rowb, kind, k, ef, out_keys.data_ptr(), out_dists.data_ptr(),
-                                    out_counts.data_ptr(), stream.cuda_stream)
-            torch.cuda.synchronize()
-            st0 = idx.last_stats()
-            gk = out_keys.cpu().numpy().astype(np.uint64)
-            gd = out_dists.cpu().numpy()
-            rk0, rd0, comp0 = first
-            parity = {"queries": B, "identical_id_rows": float(np.mean(np.all(gk == rk0, axis=1))),
-                      "identical_ids": float(np.mean(gk == rk0)),
-                      "max_rel_dist_err": float(np.max(np.abs(gd - rd0) / np.maximum(np.abs(rd0), 1e-12))),
-                      "reference_computed_distances": int(comp0), "engine_computed_distances": int(st0["computed_distances"]),
-                      "reference_recall_at_10": recall_at_k(rk0[:nrec], truth)}
+                buf = b_idx.save_buffer()
+                ridx = reflib.RefIndex(dim, wl["metric"], kind, M=wl["M"], efc=wl["efc"], ef=ef, threads=cores)
+                ridx.load_buffer(buf)
+                t_load = time.perf_counter() - t0
+                del buf
+                ridx._loaded = None
+                qh = Q.cpu().numpy()
+                spent, done, first = 0.0, 0, None
+                s = 0
+                while spent < args.cpu_seconds and s < pool:
+                    qb = qh[s * B:(s + 1) * B]
+                    t0 = time.perf_counter()
+                    rkeys, rd, rc, comp, vis = ridx.search_batch(qb, k, threads=cores)
+                    spent += time.perf_counter() - t0
+                    done += B
+                    if first is None:
+                        first = (rkeys, rd, comp)
+                    s += 1
+                cpu_qps = done / spent
+                cpu_baseline = {"value": cpu_qps, "unit": "queries/s", "cores": cores, "kind": "reference",
+                                "sample": "unmodified usearch (oracle/_ref) loads %s (%.0f s) and searches %d of the bench's query "
+                                          "batches (%d queries, %.1f s) on %d threads" % (b_what, t_load, s, done, spent, cores)}
+                # same-graph parity at that size: step-0 queries, ids position-wise
+                b_idx.search_batch_device(Q.data_ptr(), B, rowb, kind, k, ef, out_keys.data_ptr(), out_dists.data_ptr(),
+                                          out_counts.data_ptr(), stream.cuda_stream)
+                torch.cuda.synchronize()
+                st0 = b_idx.last_stats()
+                gk = out_keys.cpu().numpy().astype(np.uint64)
+                gd = out_dists.cpu().numpy()
+                rk0, rd0, comp0 = first
+                parity = {"graph_rows": b_n, "queries": B, "identical_id_rows": float(np.mean(np.all(gk == rk0, axis=1))),
+                          "identical_ids": float(np.mean(gk == rk0)),
+                          "max_rel_dist_err": float(np.max(np.abs(gd - rd0) / np.maximum(np.abs(rd0), 1e-12))),
+                          "reference_computed_distances": int(comp0), "engine_computed_distances": int(st0["computed_distances"]),
+                          "reference_recall_at_10": recall_at_k(rk0[:nrec], b_truth),
+                          "engine_recall_at_10": recall_at_k(gk[:nrec], b_truth)}
+            except Exception as e:  # the baseline is a side measurement: never lose the GPU numbers over it
+                cpu_note = "cpu_baseline failed: %r" % (e,)
+                print(cpu_note, file=sys.stderr)
+            finally:
+                if b_idx is not idx:
+                    b_idx.close()
 
     if world == 1 and not args.no_cpu_baseline and cpu_baseline is None and not pq:
         # oracle/_ref unavailable (or the index file too large for host RAM): the plain-C restatement on one core, on a
@@ -708,7 +759,7 @@ def run_ours(args, wl):
                        "generator": ("64 random prototypes XOR 10%% bit flips, seeds %d/%d/%d" % (SEED_P, SEED_CORPUS, SEED_QUERY)) if kind == "b1" else
                        "x = z P + %.2f eps, z~N(0,I_%d), seeds %d/%d/%d" % (NOISE, LATENT, SEED_P, SEED_CORPUS, SEED_QUERY)},
             "recall_at_10": rec if k == 10 else None, "recall_at_k": rec, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "parity": parity, "sharding": shard_info, "pq": pq_info,
+            "cpu_baseline": cpu_baseline, "cpu_baseline_note": cpu_note, "parity": parity, "sharding": shard_info, "pq": pq_info,
             "build": {"vectors_per_s": (hi - lo) / t_build, "seconds": t_build, "datagen_seconds": t_gen},
         }
         print(json.dumps(line))
@@ -723,7 +774,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--query-pool", type=int, default=32, help="distinct query batches (cycled over the steps)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("LB200_WORKLOAD", "cfg2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("LB200_WORKLOAD", "cfg3"), choices=sorted(WORKLOADS))
     ap.add_argument("--shard-ef", type=int, default=0,
                     help="--gpus > 1: per-shard ef; 0 = recall-matched (smallest ef_s whose merged recall reaches the unsharded "
                          "1-GPU recall at the workload's ef), -1 = same ef as the workload")
@@ -732,6 +783,8 @@ def main():
     ap.add_argument("--replicated-comparison", action="store_true", help="--gpus > 1: force the replicated comparison")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="bound on the cpu_baseline search time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-prefix-rows", type=int, default=1_000_000,
+                    help="corpora above 8 GB: rows of the prefix graph the engine builds for the reference to load (cpu_baseline)")
     ap.add_argument("--search-expand", type=int, default=1, help="candidates expanded per search round (1 = the reference's exact order)")
     ap.add_argument("--pq-ref-rows", type=int, default=100_000, help="pq workloads: rows the reference indexes for cpu_baseline")
     ap.add_argument("--ref-seconds", type=float, default=60.0, help="--impl reference: target duration of the K timed steps")
