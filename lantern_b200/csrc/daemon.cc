@@ -170,6 +170,13 @@ struct Daemon {
             if (magic != kMagicQuery || !read_exact(fd, hdr, sizeof(hdr)))
                 break;
             const uint32_t k = hdr[0], ef = hdr[1], flags = hdr[2], nbytes = hdr[3];
+            if (nbytes > std::max<size_t>(qbytes, 1u << 16)) { // never size a buffer from an unchecked wire field
+                const std::string msg = "query body too large for this index";
+                uint32_t head[2] = {1u, (uint32_t)msg.size()};
+                if (write_all(fd, head, sizeof(head)))
+                    write_all(fd, msg.data(), msg.size());
+                break; // the stream cannot be resynchronised without reading the body: drop the connection
+            }
             std::vector<uint8_t> body(nbytes);
             if (nbytes && !read_exact(fd, body.data(), nbytes))
                 break;
@@ -282,6 +289,7 @@ int main(int argc, char** argv) {
             return 2;
         }
     }
+    d.max_batch = std::max<size_t>(d.max_batch, 1);
     if (index_path.empty() || !dims || (sock_path.empty() && !port)) {
         fprintf(stderr, "need --index, --dim and one of --socket / --port\n");
         return 2;
@@ -343,7 +351,14 @@ int main(int argc, char** argv) {
         }
         int one = 1;
         setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
-        std::thread([&d, fd] { d.serve(fd); }).detach();
+        std::thread([&d, fd] {
+            try {
+                d.serve(fd);
+            } catch (const std::exception& e) { // e.g. bad_alloc: lose the connection, not the daemon
+                fprintf(stderr, "lb200_search_daemon: connection dropped: %s\n", e.what());
+                close(fd);
+            }
+        }).detach();
     }
     d.stop = true;
     d.cv.notify_all();

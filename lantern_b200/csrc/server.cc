@@ -87,6 +87,13 @@ void serve(Conn& c, bool verbose) {
                    ef = init[7], num_centroids = init[8], num_subvectors = init[9], capacity = init[10], element_bits = init[11];
     if (quantization > 5)
         throw std::runtime_error("Invalid scalar quantization");
+    // everything below sizes buffers from these fields: refuse nonsense before allocating (the library re-checks the rest)
+    if (dim == 0 || dim > 65536)
+        throw std::runtime_error("vector dimensions must be in [1, 65536]");
+    if (element_bits >= 8 && element_bits != 32)
+        throw std::runtime_error("only 32-bit float rows (or packed bits) are accepted");
+    if (pq == 1 && (num_centroids == 0 || num_centroids > 256 || num_subvectors == 0))
+        throw std::runtime_error("pq needs 1..256 centroids and a nonzero number of subvectors");
 
     std::vector<float> codebook;
     if (pq == 1) { // frames of dim floats until END_MSG (server.rs:109-130)
@@ -97,6 +104,8 @@ void serve(Conn& c, bool verbose) {
             memcpy(&head, frame.data(), 4);
             if (head == kEndMsg)
                 break;
+            if (codebook.size() >= (size_t)num_centroids * dim)
+                throw std::runtime_error("codebook has more rows than num_centroids");
             c.read_exact(frame.data() + 4, frame.size() - 4);
             const float* f = (const float*)frame.data();
             codebook.insert(codebook.end(), f, f + dim);
@@ -130,8 +139,6 @@ void serve(Conn& c, bool verbose) {
     // rows (server.rs:226-263): element_bits < 8 -> packed bits, else dim * element_bits/8 bytes
     const size_t vec_bytes = element_bits < 8 ? ((size_t)dim + 7) / 8 : (size_t)dim * (element_bits / 8);
     const lb200_scalar_kind_t in_kind = element_bits < 8 ? lb200_scalar_b1_k : lb200_scalar_f32_k;
-    if (element_bits >= 8 && element_bits != 32)
-        throw std::runtime_error("only 32-bit float rows (or packed bits) are accepted");
     const size_t frame_bytes = 8 + vec_bytes;
     std::vector<uint8_t> frame(frame_bytes);
     std::vector<uint64_t> keys;
@@ -210,6 +217,10 @@ int main(int argc, char** argv) {
     }
     signal(SIGPIPE, SIG_IGN);
     int ls = socket(AF_INET, SOCK_STREAM, 0);
+    if (ls < 0) {
+        fprintf(stderr, "cannot create a socket: %s\n", strerror(errno));
+        return 1;
+    }
     int one = 1;
     setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
     sockaddr_in addr;
