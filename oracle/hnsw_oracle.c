@@ -760,6 +760,178 @@ int ora_add(ora_index* x, uint64_t key, const void* vector, int kind, int level,
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Model of the CUDA engine's BATCHED build (lantern_b200/csrc/build.cu) -- not a reference function.
+ * The reference inserts one node at a time; the engine inserts batches in two phases so that thousands of inserts
+ * run concurrently.  This restates that schedule on top of the reference procedures above, so that the engine's
+ * default build can be checked bit for bit against a CPU specification (tests/test_gpu_build.py) instead of only
+ * statistically (recall):
+ *   levels are drawn up front for all pending vectors (same generator, same order as sequential inserts);
+ *   a batch holds min(remaining, batch_cap, max(1, visible / build_ratio)) nodes and is cut in front of a node whose
+ *   level exceeds the current top level (such a node is inserted alone and then becomes the entry point);
+ *   phase 1, per node of the batch, all against the graph as it was BEFORE the batch: greedy descent, efc-wide beam
+ *   and heuristic per level (search_to_insert + refine, exactly as in ora_add), own lists written, one reverse-link
+ *   request (level, target, distance, new node) per selected neighbour;
+ *   phase 2: requests grouped by (level, target) in (node, position) order -- a stable sort, as the radix sort of the
+ *   engine is -- and applied one after the other: append while the list has room, else re-prune {new} + list with the
+ *   heuristic.  Distances target->neighbour are measured once per group, when it first overflows; entries kept by a
+ *   re-prune carry their distance to the next request of the same group.
+ * With batch_cap == 1 this is ora_add (byte-identical index file; tests/test_oracle_ref.py).  PQ indexes are not
+ * modelled (a carried distance of a new node is value-vs-stored there, a re-measured one stored-vs-stored).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    uint64_t key; /* (level << 32) | target */
+    float d;
+    uint32_t u;
+} req_t;
+
+static void reqs_stable_sort(req_t* a, req_t* tmp, size_t n) { /* bottom-up merge sort by key: stable */
+    size_t w, i;
+    for (w = 1; w < n; w *= 2) {
+        for (i = 0; i < n; i += 2 * w) {
+            size_t l = i, m = i + w < n ? i + w : n, r = i + 2 * w < n ? i + 2 * w : n, a0 = l, b0 = m, o = l;
+            while (a0 < m && b0 < r)
+                tmp[o++] = a[b0].key < a[a0].key ? a[b0++] : a[a0++];
+            while (a0 < m)
+                tmp[o++] = a[a0++];
+            while (b0 < r)
+                tmp[o++] = a[b0++];
+        }
+        memcpy(a, tmp, n * sizeof(req_t));
+    }
+}
+
+int ora_add_batch_engine(ora_index* x, const uint64_t* keys, const void* vectors, size_t n, size_t stride, int kind,
+                         size_t batch_cap, size_t build_ratio) {
+    if (x->pq)
+        return -2;
+    if (x->n + n > x->cap)
+        return -1;
+    if (!n)
+        return 0;
+    if (!batch_cap)
+        batch_cap = 1;
+    if (!build_ratio)
+        build_ratio = 1;
+    const size_t n0 = x->n, P = n, M = x->M, M0 = x->M0;
+    size_t i, pos = 0;
+    /* node records of all pending vectors: the engine stores them at insertion ids n0.. before the first batch */
+    for (i = 0; i < P; ++i) {
+        const size_t slot = n0 + i;
+        const void* value = cast_input(x, (const uint8_t*)vectors + i * stride, kind);
+        int target = choose_random_level(&x->rng, M);
+        x->keys[slot] = keys[i];
+        x->levels[slot] = (int16_t)target;
+        x->cnt0[slot] = 0;
+        memset(x->nbr0 + slot * M0, 0, M0 * sizeof(uint32_t));
+        x->upper[slot] = target > 0 ? (uint32_t*)calloc((size_t)target * (1 + M), sizeof(uint32_t)) : NULL;
+        memcpy(x->vectors + slot * x->stored_bytes, value, x->stored_bytes);
+    }
+    x->n = n0 + P; /* records exist (ora_free walks them); visibility is governed by entry / links below */
+    size_t visible = n0;
+    if (n0 == 0) { /* first node: entry point, no links (index.hpp:2538-2543) */
+        x->entry = 0, x->max_level = x->levels[0];
+        visible = 1, pos = 1;
+    }
+    req_t *reqs = NULL, *tmp = NULL;
+    size_t reqs_cap = 0;
+    float* dist = (float*)malloc((M0 + 2) * sizeof(float));
+    while (pos < P) {
+        size_t bsz = 1;
+        if (x->levels[n0 + pos] <= x->max_level) {
+            size_t ramp = visible / build_ratio;
+            if (ramp < 1)
+                ramp = 1;
+            bsz = P - pos;
+            if (bsz > batch_cap)
+                bsz = batch_cap;
+            if (bsz > ramp)
+                bsz = ramp;
+            for (i = 1; i < bsz; ++i)
+                if (x->levels[n0 + pos + i] > x->max_level) {
+                    bsz = i;
+                    break;
+                }
+        }
+        const int max_level = x->max_level;
+        const uint32_t entry = (uint32_t)x->entry;
+        const size_t need = bsz * M * (size_t)(max_level + 1);
+        if (need > reqs_cap) {
+            reqs_cap = need * 2;
+            reqs = (req_t*)realloc(reqs, reqs_cap * sizeof(req_t));
+            tmp = (req_t*)realloc(tmp, reqs_cap * sizeof(req_t));
+        }
+        size_t nreq = 0, b;
+        /* ---- phase 1: every node of the batch against the graph before the batch ---- */
+        for (b = 0; b < bsz; ++b) {
+            const uint32_t slot = (uint32_t)(n0 + pos + b);
+            const int lu = x->levels[slot];
+            const void* value = x->vectors + (size_t)slot * x->stored_bytes; /* cast value == stored vector (no pq) */
+            uint32_t closest = search_for_one(x, value, entry, max_level, lu);
+            int l;
+            for (l = lu < max_level ? lu : max_level; l >= 0; --l) {
+                search_to_insert(x, value, closest, slot, l, x->efc);
+                size_t view = refine(x, M), t;
+                uint32_t* cnt;
+                uint32_t* mine = nbr_list(x, slot, l, &cnt);
+                for (t = 0; t < view; ++t) {
+                    mine[(*cnt)++] = x->top.e[t].s;
+                    reqs[nreq].key = ((uint64_t)(uint32_t)l << 32) | x->top.e[t].s;
+                    reqs[nreq].d = x->top.e[t].d, reqs[nreq].u = slot;
+                    nreq++;
+                }
+                closest = mine[0];
+            }
+        }
+        /* ---- phase 2: reverse links, grouped by (level, target), in (node, position) order ---- */
+        reqs_stable_sort(reqs, tmp, nreq);
+        size_t r = 0;
+        while (r < nreq) {
+            const uint64_t key = reqs[r].key;
+            const int level = (int)(key >> 32);
+            const uint32_t v = (uint32_t)key;
+            const size_t cmax = level ? M : M0;
+            uint32_t* ccnt;
+            uint32_t* cl = nbr_list(x, v, level, &ccnt);
+            int have_d = 0;
+            for (; r < nreq && reqs[r].key == key; ++r) {
+                const uint32_t u = reqs[r].u;
+                const float d_uv = reqs[r].d;
+                uint32_t k;
+                if (*ccnt < cmax) { /* index.hpp:3186-3189 */
+                    dist[*ccnt] = d_uv;
+                    cl[(*ccnt)++] = u;
+                    continue;
+                }
+                if (!have_d) { /* distances target -> each current neighbour (index.hpp:3196-3198) */
+                    for (k = 0; k < *ccnt; ++k)
+                        dist[k] = measure_vv(x, v, cl[k]);
+                    have_d = 1;
+                }
+                x->top.n = 0;
+                sbuf_insert_reserved(&x->top, d_uv, u);
+                for (k = 0; k < *ccnt; ++k)
+                    sbuf_insert_reserved(&x->top, dist[k], cl[k]);
+                memset(cl, 0, *ccnt * sizeof(uint32_t));
+                *ccnt = 0;
+                size_t v2 = refine(x, cmax), t;
+                for (t = 0; t < v2; ++t) {
+                    dist[*ccnt] = x->top.e[t].d;
+                    cl[(*ccnt)++] = x->top.e[t].s;
+                }
+            }
+        }
+        visible += bsz;
+        if (x->levels[n0 + pos] > x->max_level) { /* index.hpp:2558-2562 */
+            x->entry = n0 + pos;
+            x->max_level = x->levels[n0 + pos];
+        }
+        pos += bsz;
+    }
+    free(reqs), free(tmp), free(dist);
+    return 0;
+}
+
 /* index_gt::search, index.hpp:2680-2730. */
 size_t ora_search(ora_index* x, const void* query, int kind, size_t k, size_t ef, uint64_t* keys, float* distances,
                   ora_stats* stats) {

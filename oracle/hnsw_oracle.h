@@ -49,6 +49,12 @@ uint64_t ora_entry_slot(const ora_index*);
  * level < 0 -> drawn from the reference's generator (index.hpp:3208-3212, std::default_random_engine). */
 int ora_add(ora_index*, uint64_t key, const void* vector, int kind, int level, ora_stats* stats);
 
+/* Model of the CUDA engine's batched build schedule on top of the reference procedures (NOT a reference function; see
+ * the .c file): `n` vectors, `stride` bytes apart, inserted in batches of at most `batch_cap` nodes and at most
+ * visible/build_ratio.  batch_cap == 1 is ora_add.  Returns 0, -1 (capacity), -2 (pq not modelled). */
+int ora_add_batch_engine(ora_index*, const uint64_t* keys, const void* vectors, size_t n, size_t stride, int kind,
+                         size_t batch_cap, size_t build_ratio);
+
 /* ef == 0 -> index default; expansion = max(ef, k) (index.hpp:2706). Returns found count. */
 size_t ora_search(ora_index*, const void* query, int kind, size_t k, size_t ef, uint64_t* keys, float* distances,
                   ora_stats* stats);

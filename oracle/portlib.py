@@ -47,6 +47,8 @@ def lib():
         L.ora_entry_slot.restype = C.c_uint64
         L.ora_entry_slot.argtypes = [C.c_void_p]
         L.ora_add.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.POINTER(Stats)]
+        L.ora_add_batch_engine.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t,
+                                           C.c_size_t]
         L.ora_search.restype = C.c_size_t
         L.ora_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
                                  C.POINTER(Stats)]
@@ -117,6 +119,15 @@ class PortIndex:
         if rc:
             raise RuntimeError("ora_add failed: %d" % rc)
         return st
+
+    def add_batch_engine(self, keys, vecs, batch_cap, build_ratio=64):
+        """Model of the CUDA engine's batched build schedule (hnsw_oracle.c: ora_add_batch_engine); batch_cap=1 == add()."""
+        vecs = np.ascontiguousarray(vecs)
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        rc = lib().ora_add_batch_engine(self.h, keys.ctypes.data, vecs.ctypes.data, len(vecs), vecs.strides[0], self._kind(vecs),
+                                        int(batch_cap), int(build_ratio))
+        if rc:
+            raise RuntimeError("ora_add_batch_engine failed: %d" % rc)
 
     def search(self, q, k, ef=0):
         q = np.ascontiguousarray(q)

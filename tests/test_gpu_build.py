@@ -1,4 +1,6 @@
 """GPU parity of the build path (lb200_add* + lb200_build) against the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -42,6 +44,32 @@ def test_exact_order_build_is_byte_identical(eng, port, metric, d, M, efc):
     if not np.array_equal(gb, pb):
         # ties inside the candidate queue can reorder equal-distance expansions; demand near-identity
         assert np.mean(gb == pb) > 0.995
+
+
+@pytest.mark.skipif(not os.environ.get("LB200_UNVALIDATED"),
+                    reason="written at the end of round 1 without GPU access: run once with LB200_UNVALIDATED=1, then un-gate")
+@pytest.mark.parametrize("metric,d,M,efc,batch", [("l2sq", 48, 8, 64, 64), ("cos", 32, 16, 128, 256)])
+def test_batched_build_follows_the_cpu_model(eng, port, metric, d, M, efc, batch):
+    """The DEFAULT (batched, two-phase) build against its CPU specification, oracle ora_add_batch_engine: same batch
+    schedule (build_batch / build_ratio), same phase-1 searches against the pre-batch graph, same stable request order in
+    phase 2 -> the same index file on integer-valued data (up to the tie order inside the candidate queue, as in the
+    sequential case above)."""
+    rng = np.random.default_rng(19)
+    n = 3000
+    X = rng.integers(-8, 9, (n, d)).astype(np.float32)
+    keys = np.arange(1, n + 1, dtype=np.uint64)
+    p = port.PortIndex(d, metric, "f32", M=M, efc=efc, ef=32)
+    p.reserve(n)
+    p.add_batch_engine(keys, X, batch, 64)
+    g = eng.Index(d, metric, "f32", M=M, efc=efc, ef=32)
+    g.set_option("build_batch", batch)
+    g.set_option("build_ratio", 64)
+    g.reserve(n)
+    g.add_batch(keys, X)
+    g.build()
+    gb, pb = g.save_buffer(), p.save_buffer()
+    assert len(gb) == len(pb)
+    assert np.mean(gb == pb) > 0.995
 
 
 def test_batched_build_recall_matches_reference_graph(eng, port):

@@ -137,3 +137,57 @@ def test_property_port_equals_reference_on_random_small_configs(port, ref):
             assert np.array_equal(rk, pk) and np.array_equal(rd, pd)
 
     check()
+
+
+@pytest.mark.parametrize("metric,quant", [("l2sq", "f32"), ("cos", "f32"), ("hamming", "b1")])
+def test_batched_build_model_with_batches_of_one_is_sequential_insertion(port, metric, quant):
+    """ora_add_batch_engine models the CUDA engine's two-phase batched build on top of the reference procedures
+    (hnsw_oracle.c).  With batch_cap = 1 it must BE the reference's sequential insertion: byte-identical index file."""
+    rng = np.random.default_rng(23)
+    n = 1500
+    if quant == "b1":
+        X, dim = rng.integers(0, 256, (n, 24), dtype=np.uint8), 192
+    else:
+        X, dim = rng.integers(-8, 9, (n, 24)).astype(np.float32), 24
+    keys = np.arange(1, n + 1, dtype=np.uint64)
+    a = port.PortIndex(dim, metric, quant, M=8, efc=48, ef=32)
+    a.reserve(n)
+    for k, v in zip(keys, X):
+        a.add(int(k), v)
+    b = port.PortIndex(dim, metric, quant, M=8, efc=48, ef=32)
+    b.reserve(n)
+    b.add_batch_engine(keys[:700], X[:700], 1)   # two calls: the level generator carries over like in ora_add
+    b.add_batch_engine(keys[700:], X[700:], 1)
+    assert np.array_equal(a.save_buffer(), b.save_buffer())
+
+
+def test_batched_build_model_is_deterministic_and_as_good_as_sequential(port):
+    rng = np.random.default_rng(29)
+    n, d = 4000, 24
+    X = rng.integers(-8, 9, (n, d)).astype(np.float32)
+    Q = rng.integers(-8, 9, (300, d)).astype(np.float32)
+    keys = np.arange(1, n + 1, dtype=np.uint64)
+    truth, _ = port.exact_search(X, Q, 10)
+
+    def rec(idx):
+        k, _, _, _ = idx.search_batch(Q, 10)
+        return float(np.mean([len(set(a.tolist()) & set((t + 1).tolist())) / 10.0 for a, t in zip(k, truth)]))
+
+    seq = port.PortIndex(d, "l2sq", "f32", M=8, efc=48, ef=32)
+    seq.reserve(n)
+    for k, v in zip(keys, X):
+        seq.add(int(k), v)
+    files = []
+    for _ in range(2):
+        b = port.PortIndex(d, "l2sq", "f32", M=8, efc=48, ef=32)
+        b.reserve(n)
+        b.add_batch_engine(keys, X, 64, 64)
+        files.append(b.save_buffer())
+    assert np.array_equal(files[0], files[1])
+    assert len(files[0]) == len(seq.save_buffer())  # same level draws -> same file size
+    assert abs(rec(b) - rec(seq)) < 0.02
+    # every link of the batched graph points to a node that exists on that level (what lb200_load_buffer verifies)
+    for slot in range(0, n, 97):
+        for level in range(b.level(slot) + 1):
+            for nb in b.neighbors(slot, level):
+                assert b.level(int(nb)) >= level
