@@ -5,9 +5,13 @@ import numpy as np
 import pytest
 
 
-def trim(buf):
+def trim(buf, stored_bytes=None):
+    """The reference's save_buffer may leave slack after the last node; pq nodes carry `num_subvectors` code bytes instead
+    of the header's vector_size_bytes."""
     n, M, M0 = struct.unpack_from("<QQQ", buf, 80)
     vsz, = struct.unpack_from("<Q", buf, 120)
+    if stored_bytes is not None:
+        vsz = stored_bytes
     off, b = 136, bytes(buf)
     for _ in range(n):
         lvl, = struct.unpack_from("<h", b, off + 8)
@@ -132,6 +136,47 @@ def test_property_port_equals_reference_on_random_small_configs(port, ref):
         assert np.array_equal(trim(r.save_buffer()), p.save_buffer())
         for q in rng.integers(-5, 6, (10, d)).astype(np.float32):
             k = int(rng.integers(1, 12))
+            rk, rd = r.search(q, k)
+            pk, pd, _ = p.search(q, k)
+            assert np.array_equal(rk, pk) and np.array_equal(rd, pd)
+
+    check()
+
+
+def test_property_scalar_kinds_bits_and_pq(port, ref):
+    """Same property for the storage variants: f16 / i8 scalar quantisation (f32 in, cast on add), packed bits with the
+    hamming metric, and pq storage with a random codebook (stored side decoded, value side raw)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=20, deadline=None)
+    @given(n=st.integers(2, 200), sub=st.integers(1, 6), M=st.sampled_from([2, 4, 8]), efc=st.integers(4, 48),
+           ef=st.integers(1, 32), variant=st.sampled_from(["f16", "i8", "b1", "pq"]), metric=st.sampled_from(["l2sq", "cos"]),
+           seed=st.integers(0, 10_000))
+    def check(n, sub, M, efc, ef, variant, metric, seed):
+        rng = np.random.default_rng(seed)
+        kw, quant, d = {}, "f32", 4 * sub
+        if variant == "b1":
+            metric, quant, d = "hamming", "b1", 32 * sub
+            X = rng.integers(0, 256, (n, d // 8), dtype=np.uint8)
+            Q = rng.integers(0, 256, (8, d // 8), dtype=np.uint8)
+        else:
+            # small multiples of 1/4: exact in f16, and |x| * 100 stays an integer below the i8 clamp for the small ones
+            X = (rng.integers(-4, 5, (n, d)) / 4.0).astype(np.float32)
+            Q = (rng.integers(-4, 5, (8, d)) / 4.0).astype(np.float32)
+            if variant == "pq":
+                ncent = int(rng.integers(2, 9))
+                kw = dict(pq=True, num_centroids=ncent, num_subvectors=sub,
+                          codebook=(rng.integers(-4, 5, (ncent, d)) / 4.0).astype(np.float32))
+            else:
+                quant = variant
+        r = ref.RefIndex(d, metric, quant, M=M, efc=efc, ef=ef, **kw)
+        p = port.PortIndex(d, metric, quant, M=M, efc=efc, ef=ef, **kw)
+        r.reserve(n), p.reserve(n)
+        for i in range(n):
+            r.add(i + 1, X[i]), p.add(i + 1, X[i])
+        assert np.array_equal(trim(r.save_buffer(), sub if variant == "pq" else None), p.save_buffer())
+        for q in Q:
+            k = int(rng.integers(1, 10))
             rk, rd = r.search(q, k)
             pk, pd, _ = p.search(q, k)
             assert np.array_equal(rk, pk) and np.array_equal(rd, pd)
