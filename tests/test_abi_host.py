@@ -239,3 +239,20 @@ def test_page_storage_entry_points_explain_themselves():
         err = C.c_char_p()
         fn(*args, C.byref(err))
         assert err.value and b"null" in err.value
+
+
+def test_ctypes_signatures_agree_with_the_header():
+    """lantern_b200/api.py binds by hand: every prototype's parameter count (and 'returns a value or not') must match the
+    declaration in include/lantern_b200.h, or calls would silently shift arguments."""
+    from lantern_b200 import api
+    text = open(os.path.join(ROOT, "include", "lantern_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"LB200_EXPORT\s+([^;(]*?)\b(lb200_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) >= 40
+    for ret, name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        restype, argtypes = api.SIGNATURES[name]
+        assert len(argtypes) == n, (name, n, len(argtypes))
+        returns_value = ret.strip() not in ("void",)
+        assert (restype is not None) == returns_value, (name, ret)
