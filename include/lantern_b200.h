@@ -169,7 +169,9 @@ LB200_EXPORT void lb200_search_batch(lb200_index_t, void const* queries, size_t 
                                      lb200_scalar_kind_t query_kind, size_t count, size_t ef, lb200_key_t* keys,
                                      lb200_distance_t* distances, size_t* counts, lb200_error_t* error);
 /* Same with queries and outputs resident in DEVICE memory (counts: uint32_t[nq] or NULL); asynchronous on
- * `cuda_stream` (a cudaStream_t passed as void*; NULL = default stream). */
+ * `cuda_stream` (a cudaStream_t passed as void*; NULL = default stream).  One index owns one set of device scratch (query
+ * staging, visited bitmaps, work counters): asynchronous calls on the SAME index must be issued on one stream, or be ordered
+ * by the caller; different indexes are independent.  An index belongs to the device that was current in lb200_init. */
 LB200_EXPORT void lb200_search_batch_device(lb200_index_t, void const* d_queries, size_t nq, size_t stride,
                                             lb200_scalar_kind_t query_kind, size_t count, size_t ef,
                                             lb200_key_t* d_keys, lb200_distance_t* d_distances, uint32_t* d_counts,
