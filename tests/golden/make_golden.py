@@ -133,6 +133,6 @@ for M in (16, 4):
         off += 10 + 4 + 12 * M + l * (4 + 6 * M) + 8
     out["levels_M%d" % M] = np.array(lv, np.int16)
 
-path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_v1.npz")
+path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_v1.npz")
 np.savez_compressed(path, **out)
 print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")
