@@ -179,6 +179,52 @@ def recall_at_k(found, truth):
     return hits / float(truth.size)
 
 
+def usable_cores():
+    """Host threads this process may actually run on: the affinity mask, capped by the cgroup CPU quota (a container on a
+    128-core box may be limited to far fewer; std::thread::hardware_concurrency() reports the box)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def parity_block(gk, gd, rk, rd, rtol=1e-5, atol=1e-6):
+    """Same-graph parity of two result sets.  Position-wise id equality, plus a tie-aware row test: ids may be permuted
+    inside groups of (near-)equal distances (the reference's binary heap and the engine's sorted list pop equal-distance
+    candidates in different orders -- DESIGN.md 4.1), and an id may be swapped at the tail against another of the same
+    distance.  Distances are compared position-wise, which is meaningful because both lists are sorted ascending."""
+    nq = len(gk)
+    rows_ok = 0
+    for q in range(nq):
+        ka, kb, da, db = gk[q], rk[q], gd[q], rd[q]
+        if np.array_equal(ka, kb):
+            rows_ok += 1
+            continue
+        if not np.allclose(da, db, rtol=10 * rtol, atol=10 * atol):
+            continue
+        good = True
+        for i in np.nonzero(ka != kb)[0]:
+            pos = np.nonzero(ka == kb[i])[0]
+            ref_d = da[pos[0]] if len(pos) else da[-1]
+            if not np.isclose(ref_d, db[i], rtol=10 * rtol, atol=10 * atol):
+                good = False
+                break
+        rows_ok += good
+    fin = np.isfinite(rd) & np.isfinite(gd)
+    rel = np.abs(gd - rd)[fin] / np.maximum(np.abs(rd[fin]), 1e-12)
+    return {"identical_id_rows": float(np.mean(np.all(gk == rk, axis=1))), "identical_ids": float(np.mean(gk == rk)),
+            "rows_identical_up_to_distance_ties": rows_ok / float(nq),
+            "max_rel_dist_err": float(rel.max()) if rel.size else 0.0}
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -196,40 +242,27 @@ def run_reference(args, wl):
     from oracle import reflib
     if not reflib.available():
         return run_reference_port(args, wl)
-    cores = reflib.lib().refx_hardware_threads()
-    # bounded sample: a prefix of the corpus the reference can index in about `--ref-build-seconds` with all cores;
-    # the rate is measured on a pilot of 20k rows (it only falls slowly, ~log N, afterwards)
-    pilot = min(wl["n"], 20_000)
+    cores = min(usable_cores(), reflib.lib().refx_hardware_threads())
+    # bounded sample, the SAME on every box and every N: the reference builds its own graph over the first --ref-rows rows
+    # of the corpus generator (default 200 000; 10 M rows would take it the better part of an hour) with all usable host
+    # threads, then answers the bench's query batches
     gen = bits_np if wl.get("kind") == "b1" else structured_np
     nsteps = args.steps + args.warmup
     pool = min(nsteps, args.query_pool)
     Q = gen(pool * wl["batch"], wl["dim"], SEED_QUERY)
-    # rows are drawn from the corpus generator as they are needed (the reference never sees more than the prefix it can index
-    # in its build budget, so the 30 GB of cfg3 are not materialised): the pilot first, the rest once its size is known
-    Xp = gen(pilot if args.ref_rows == 0 else min(wl["n"], args.ref_rows), wl["dim"], SEED_CORPUS)
+    n_ref = min(wl["n"], args.ref_rows)
+    Xp = gen(n_ref, wl["dim"], SEED_CORPUS)
     pqkw = {}
     if wl.get("pq"):  # codebook for the reference arm: 256 corpus rows (a valid, if untrained, codebook), stated in `sample`
         nsub, ncent = wl["pq"]
         pqkw = dict(pq=True, num_centroids=ncent, num_subvectors=nsub,
                     codebook=Xp[np.random.default_rng(7).choice(len(Xp), ncent, replace=False)].copy())
     idx = reflib.RefIndex(wl["dim"], wl["metric"], wl.get("kind", "f32"), M=wl["M"], efc=wl["efc"], ef=wl["ef"], threads=cores, **pqkw)
-    pilot = min(pilot, len(Xp))
-    idx.reserve(len(Xp))
+    idx.reserve(n_ref)
     t0 = time.perf_counter()
-    idx.add_batch(np.arange(1, pilot + 1, dtype=np.uint64), Xp[:pilot], threads=cores)
-    t_pilot = time.perf_counter() - t0
-    t_build = t_pilot
-    n_ref = len(Xp)
-    if not args.ref_rows:
-        n_ref = int(min(wl["n"], max(pilot, 0.7 * (pilot / t_pilot) * args.ref_build_seconds)))
-        Xr = gen(n_ref - pilot, wl["dim"], SEED_CORPUS + 7919) if n_ref > pilot else Xp[:0]
-        idx.reserve(n_ref)  # grows the pilot's reservation (per-thread visited sets scale with it: reserve what is used)
-    else:
-        Xr = Xp[pilot:]
-    if n_ref > pilot:
-        t0 = time.perf_counter()
-        idx.add_batch(np.arange(pilot + 1, n_ref + 1, dtype=np.uint64), Xr, threads=cores)
-        t_build += time.perf_counter() - t0
+    idx.add_batch(np.arange(1, n_ref + 1, dtype=np.uint64), Xp, threads=cores)
+    t_build = time.perf_counter() - t0
+    Xr = None
     del Xp, Xr
     # each timed step is a bounded sample of the batch, sized from the warm-up rate so that K steps take about a minute
     B = wl["batch"]
@@ -246,7 +279,7 @@ def run_reference(args, wl):
         times.append(time.perf_counter() - t0)
     total = sum(times)
     value = args.steps * per_step / total
-    sample = ("reference builds its own graph over %d rows drawn from the %d-row corpus generator (%.0f s, %d threads); each step = "
+    sample = ("reference builds its own graph over the first %d rows of the %d-row corpus generator (%.0f s, %d threads); each step = "
               "the first %d queries of a %d-query batch" % (n_ref, wl["n"], t_build, cores, per_step, B))
     line = {
         "impl": "reference", "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -315,8 +348,8 @@ def run_ours(args, wl):
     kind = wl.get("kind", "f32")
     rowb = dim // 8 if kind == "b1" else dim * 4  # bytes of one input row
     gen_t = bits_torch if kind == "b1" else structured_torch
-    nsteps = args.steps + args.warmup
     args.warmup = max(3, args.warmup)  # timing rules: at least 3 warm-up steps (the JSON line reports the value used)
+    nsteps = args.steps + args.warmup  # after the clamp: exactly args.steps timed iterations
     pool = min(nsteps, args.query_pool)  # distinct query batches, cycled: step s uses batch s % pool
 
     # ---- corpus shard of this rank: contiguous row range ----
@@ -341,6 +374,8 @@ def run_ours(args, wl):
         idx.build()
         torch.cuda.synchronize()
         t_build = time.perf_counter() - t0
+        bst = idx.last_build_stats()
+        build_work = [bst["computed_distances"], bst["algorithmic_bytes"], bst["device_ms"]]
     else:
         # PQ storage (cfg4): the raw fp32 corpus (61 GB at 10M x d1536) is never resident as a whole: it is generated
         # chunk by chunk; each chunk feeds (a) the running exact top-k used as recall ground truth, (b) lb200_add_batch +
@@ -360,6 +395,7 @@ def run_ours(args, wl):
         run_k = torch.full((2, nrec, k), -1, dtype=torch.int64, device=dev)
         run_d = torch.full((2, nrec, k), float("inf"), dtype=torch.float32, device=dev)
         t_gen, t_build = 0.0, 0.0
+        build_work = [0, 0, 0.0]
         for c, clo in enumerate(range(0, n, chunk)):
             chi = min(n, clo + chunk)
             t1 = time.perf_counter()
@@ -379,6 +415,9 @@ def run_ours(args, wl):
             idx.build()
             torch.cuda.synchronize()
             t_build += time.perf_counter() - t1
+            bst = idx.last_build_stats()
+            build_work = [build_work[0] + bst["computed_distances"], build_work[1] + bst["algorithmic_bytes"],
+                          build_work[2] + bst["device_ms"]]
             del Xc
         pq_truth = run_k[0].cpu().numpy()
         pq_info = {"num_subvectors": nsub, "num_centroids": ncent, "kmeans_rounds": rounds, "kmeans_seconds": t_train,
@@ -581,7 +620,9 @@ def run_ours(args, wl):
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel": "hnsw_search_kernel<%s,%s>" % (wl["metric"], "pq" if pq else kind),
-                "kernel_ms_per_step": kern_ms / args.steps, "algorithmic_bytes_per_step": alg_bytes / args.steps,
+                "kernel_ms_per_step": kern_ms / args.steps,
+                "timing": "kernel_ms_per_step: CUDA events around the one kernel launch, in a SEPARATE pass over the same steps whose "
+                          "stats read-back synchronises after every step (slightly slower than the back-to-back `ms_per_step`)", "algorithmic_bytes_per_step": alg_bytes / args.steps,
                 "dist_evals_per_query": n_dist / (args.steps * B), "pops_per_query": pops / (args.steps * B)}
 
     # ---- e2e through the reference-facing host call: pinned host buffers in/out, copies inside the timed region ----
@@ -643,7 +684,7 @@ def run_ours(args, wl):
         # the same codebook, over a bounded prefix of the corpus and searches the bench's query batches
         from oracle import reflib
         if reflib.available():
-            cores = reflib.lib().refx_hardware_threads()
+            cores = min(usable_cores(), reflib.lib().refx_hardware_threads())
             n_ref = min(n, args.pq_ref_rows)
             Xr = gen_t(n_ref, dim, SEED_CORPUS * 1000, dev).cpu().numpy()
             ridx = reflib.RefIndex(dim, wl["metric"], M=wl["M"], efc=wl["efc"], ef=ef, threads=cores, pq=True,
@@ -670,7 +711,7 @@ def run_ours(args, wl):
         if reflib.available():
             b_idx = idx
             try:
-                cores = reflib.lib().refx_hardware_threads()
+                cores = min(usable_cores(), reflib.lib().refx_hardware_threads())
                 b_n, b_truth, b_what = n, truth, "the engine's %d-node index file" % n
                 if n * rowb > BIG_CORPUS_BYTES:
                     # The reference needs the index file twice in host RAM (35 GB each for cfg3) and half a minute to parse it:
@@ -721,12 +762,11 @@ def run_ours(args, wl):
                 gk = out_keys.cpu().numpy().astype(np.uint64)
                 gd = out_dists.cpu().numpy()
                 rk0, rd0, comp0 = first
-                parity = {"graph_rows": b_n, "queries": B, "identical_id_rows": float(np.mean(np.all(gk == rk0, axis=1))),
-                          "identical_ids": float(np.mean(gk == rk0)),
-                          "max_rel_dist_err": float(np.max(np.abs(gd - rd0) / np.maximum(np.abs(rd0), 1e-12))),
-                          "reference_computed_distances": int(comp0), "engine_computed_distances": int(st0["computed_distances"]),
-                          "reference_recall_at_10": recall_at_k(rk0[:nrec], b_truth),
-                          "engine_recall_at_10": recall_at_k(gk[:nrec], b_truth)}
+                parity = {"graph_rows": b_n, "queries": B}
+                parity.update(parity_block(gk, gd, rk0, rd0))
+                parity.update({"reference_computed_distances": int(comp0), "engine_computed_distances": int(st0["computed_distances"]),
+                               "reference_recall_at_10": recall_at_k(rk0[:nrec], b_truth),
+                               "engine_recall_at_10": recall_at_k(gk[:nrec], b_truth)})
             except Exception as e:  # the baseline is a side measurement: never lose the GPU numbers over it
                 cpu_note = "cpu_baseline failed: %r" % (e,)
                 print(cpu_note, file=sys.stderr)
@@ -760,7 +800,12 @@ def run_ours(args, wl):
                        "x = z P + %.2f eps, z~N(0,I_%d), seeds %d/%d/%d" % (NOISE, LATENT, SEED_P, SEED_CORPUS, SEED_QUERY)},
             "recall_at_10": rec if k == 10 else None, "recall_at_k": rec, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "cpu_baseline_note": cpu_note, "parity": parity, "sharding": shard_info, "pq": pq_info,
-            "build": {"vectors_per_s": (hi - lo) / t_build, "seconds": t_build, "datagen_seconds": t_gen},
+            "build": {"vectors_per_s": (hi - lo) / t_build, "seconds": t_build, "datagen_seconds": t_gen,
+                      # SURVEY 8d build metric: sum of computed_distances(add) x bytes per stored vector / device time
+                      "dist_evals_per_vector": build_work[0] / max(1, hi - lo), "device_seconds": build_work[2] / 1e3,
+                      "roofline": {"bound": "hbm+l2 (the heuristic re-reads rows that mostly hit L2)",
+                                   "achieved": build_work[1] / max(build_work[2] / 1e3, 1e-9) / 1e9, "peak": peaks()[0], "unit": "GB/s",
+                                   "frac": build_work[1] / max(build_work[2] / 1e3, 1e-9) / 1e9 / peaks()[0]}},
         }
         print(json.dumps(line))
     if world > 1:
@@ -788,8 +833,8 @@ def main():
     ap.add_argument("--search-expand", type=int, default=1, help="candidates expanded per search round (1 = the reference's exact order)")
     ap.add_argument("--pq-ref-rows", type=int, default=100_000, help="pq workloads: rows the reference indexes for cpu_baseline")
     ap.add_argument("--ref-seconds", type=float, default=60.0, help="--impl reference: target duration of the K timed steps")
-    ap.add_argument("--ref-build-seconds", type=float, default=75.0, help="--impl reference: budget for the reference's own build")
-    ap.add_argument("--ref-rows", type=int, default=0, help="--impl reference: corpus prefix to index (0 = auto by core count)")
+    ap.add_argument("--ref-rows", type=int, default=200_000,
+                    help="--impl reference: corpus prefix the reference indexes (fixed, so the arm is the same on every box and N)")
     ap.add_argument("--per-step-stats", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

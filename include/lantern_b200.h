@@ -112,6 +112,15 @@ typedef struct lb200_search_stats_t {
     double kernel_ms;            /* device time of the search kernel alone (CUDA events on the launching stream) */
 } lb200_search_stats_t;
 
+/* Work of the most recent lb200_build (or implicit build): the build metric of SURVEY.md 8d is
+ * computed_distances x bytes per stored vector / seconds (counters as index.hpp:2546-2556 accumulates them per add). */
+typedef struct lb200_build_stats_t {
+    uint64_t vectors;            /* nodes inserted by that build */
+    uint64_t computed_distances; /* distance evaluations of the insert + reverse-link kernels */
+    uint64_t algorithmic_bytes;  /* computed_distances * bytes per stored vector (PQ: code bytes) */
+    double device_ms;            /* CUDA events around the whole build on its stream */
+} lb200_build_stats_t;
+
 /* ---- lifecycle: U/c/usearch.h:140-146, lib.cpp:130-176 ---------------------------------------- */
 /* `codebook` (float[num_centroids][dimensions]) is copied to the device (the reference borrows it). */
 LB200_EXPORT lb200_index_t lb200_init(lb200_init_options_t* options, float* codebook, lb200_error_t* error);
@@ -143,6 +152,7 @@ LB200_EXPORT void lb200_add_batch_device(lb200_index_t, lb200_key_t const* host_
 /* Inserts every staged vector into the HNSW graph on the GPU (index.hpp:2479-2564 semantics:
  * level draw, efc-wide beam per level, heuristic neighbour selection, reverse links with re-pruning). */
 LB200_EXPORT void lb200_build(lb200_index_t, lb200_error_t* error);
+LB200_EXPORT void lb200_last_build_stats(lb200_index_t, lb200_build_stats_t* stats, lb200_error_t* error);
 
 /* Engine knobs that have no counterpart in usearch_init_options_t:
  *   "build_batch"  max vectors inserted concurrently per batch (default 0 = one per resident CTA); 1 = strictly sequential insertion,

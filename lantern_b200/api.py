@@ -57,6 +57,11 @@ class SearchStats(C.Structure):
                 ("upper_hops", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("kernel_ms", C.c_double)]
 
 
+class BuildStats(C.Structure):
+    _fields_ = [("vectors", C.c_uint64), ("computed_distances", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
+                ("device_ms", C.c_double)]
+
+
 ERRP = C.POINTER(C.c_char_p)
 
 # name -> (restype, argtypes); the same table drives the symbol-export test
@@ -75,6 +80,7 @@ SIGNATURES = {
     "lb200_add_batch": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, ERRP]),
     "lb200_add_batch_device": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, ERRP]),
     "lb200_build": (None, [C.c_void_p, ERRP]),
+    "lb200_last_build_stats": (None, [C.c_void_p, C.POINTER(BuildStats), ERRP]),
     "lb200_set_option": (None, [C.c_void_p, C.c_char_p, C.c_size_t, ERRP]),
     "lb200_search_ef": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_bool, C.c_void_p,
                                       C.c_void_p, ERRP]),
@@ -223,6 +229,11 @@ class Index:
 
     def build(self):
         self._call("lb200_build")
+
+    def last_build_stats(self):
+        s = BuildStats()
+        self._call("lb200_last_build_stats", C.byref(s))
+        return {f: getattr(s, f) for f, _ in BuildStats._fields_}
 
     def set_option(self, name, value):
         self._call("lb200_set_option", name.encode(), int(value))

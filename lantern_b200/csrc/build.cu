@@ -226,7 +226,29 @@ template <typename T> struct DevBuf {
 
 } // namespace
 
+static void build_pending_impl(Index& idx);
+
+// Bookkeeping is transactional: if anything below throws (out of memory, launch failure) the level generator, the level /
+// list counters and the node count are put back, so that a retry draws the same levels and inserts the same nodes again
+// instead of double-inserting (pending_n_ is only cleared on success).
 void build_pending(Index& idx) {
+    if (!idx.pending_n_)
+        return;
+    const uint32_t rng0 = idx.level_rng_;
+    const size_t n0 = idx.n_, lists0 = idx.upper_lists_;
+    const int32_t max_level0 = idx.max_level_;
+    const uint32_t entry0 = idx.entry_;
+    try {
+        build_pending_impl(idx);
+    } catch (...) {
+        idx.level_rng_ = rng0, idx.n_ = n0, idx.upper_lists_ = lists0, idx.max_level_ = max_level0, idx.entry_ = entry0;
+        idx.h_levels_.resize(n0);
+        (void)cudaGetLastError();
+        throw;
+    }
+}
+
+static void build_pending_impl(Index& idx) {
     const size_t P = idx.pending_n_;
     if (!P)
         return;
@@ -290,6 +312,10 @@ void build_pending(Index& idx) {
     DevBuf<uint32_t> seg_start, nseg;
     DevBuf<uint8_t> cub_tmp;
     nseg.ensure(1);
+
+    // work counters of this build (SURVEY 8d build metric: sum of computed_distances(add) x row bytes / time)
+    LB_CUDA(cudaMemsetAsync(idx.scratch_.counters, 0, 4 * sizeof(unsigned long long), stream));
+    LB_CUDA(cudaEventRecord(idx.ev0_, stream));
 
     size_t pos = 0;
     if (n0 == 0) { // first node: entry point, no links (index.hpp:2538-2543)
@@ -373,8 +399,17 @@ void build_pending(Index& idx) {
         }
         pos += bsz;
     }
-    idx.pending_n_ = 0;
+    LB_CUDA(cudaEventRecord(idx.ev1_, stream));
     LB_CUDA(cudaStreamSynchronize(stream));
+    idx.pending_n_ = 0;
+    {
+        unsigned long long c[4] = {0, 0, 0, 0};
+        LB_CUDA(cudaMemcpy(c, idx.scratch_.counters, sizeof(c), cudaMemcpyDeviceToHost));
+        float ms = 0.f;
+        LB_CUDA(cudaEventElapsedTime(&ms, idx.ev0_, idx.ev1_));
+        idx.last_build_ms_ = ms, idx.last_build_dist_ = c[1], idx.last_build_n_ = P;
+        idx.last_nq_ = 0; // the events now bracket a build, not a search
+    }
     if (idx.d_pending_raw_) { // raw rows are only needed while inserting
         LB_CUDA(cudaFree(idx.d_pending_raw_));
         idx.d_pending_raw_ = nullptr, idx.pending_raw_cap_ = 0;

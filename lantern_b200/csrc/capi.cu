@@ -84,8 +84,9 @@ LB200_EXPORT lb200_index_t lb200_init(lb200_init_options_t* options, float* code
         require_device();
         if (options->metric)
             throw CudaError("custom metric callbacks cannot run on the GPU");
-        if (options->retriever || options->retriever_mut)
-            throw CudaError("external node retrievers are not supported: load the index file with lb200_load_buffer");
+        // options->retriever / retriever_mut / retriever_ctx: Lantern's build.c:512-517 always fills them before usearch_init
+        // ("retrievers are not called from here"); they only matter to usearch_view_mem_lazy / usearch_add_external, which
+        // refuse on their own.  Accepted and ignored here so that build.c runs unchanged.
         if (options->multi)
             throw CudaError("multi-vector keys are not supported");
         if (options->pq) { // U/c/lib.cpp:135-140, lantern_storage.hpp:90-94
@@ -211,6 +212,19 @@ LB200_EXPORT void lb200_add_batch_device(lb200_index_t h, lb200_key_t const* hos
 
 LB200_EXPORT void lb200_build(lb200_index_t h, lb200_error_t* error) {
     guarded(error, [&] { as_index(h)->build(); });
+}
+
+LB200_EXPORT void lb200_last_build_stats(lb200_index_t h, lb200_build_stats_t* stats, lb200_error_t* error) {
+    guarded(error, [&] {
+        if (!stats)
+            throw CudaError("null stats pointer");
+        Index* idx = as_index(h);
+        std::lock_guard<std::mutex> g(idx->mu_);
+        stats->vectors = idx->last_build_n_;
+        stats->computed_distances = idx->last_build_dist_;
+        stats->algorithmic_bytes = idx->last_build_dist_ * (idx->cfg_.pq ? idx->stored_bytes_ : idx->vec_bytes_);
+        stats->device_ms = idx->last_build_ms_;
+    });
 }
 
 LB200_EXPORT void lb200_set_option(lb200_index_t h, char const* name, size_t value, lb200_error_t* error) {

@@ -95,6 +95,7 @@ class Index {
 
     // usearch/lantern file format (format.cc)
     size_t serialized_length();
+    size_t serialized_length_locked(); // caller holds mu_
     size_t save_buffer(void* buffer, size_t length);
     void load_buffer(const void* buffer, size_t length);
     void write_header(void* headerp);      // 136 bytes (usearch_update_header)
@@ -122,6 +123,7 @@ class Index {
     size_t search_expand_ = 1;  // 1 = exact-order search; 2..4 = relaxed order (see walk.cuh)
     double last_build_ms_ = 0;
     uint64_t last_build_dist_ = 0;
+    size_t last_build_n_ = 0;
 
     // device arrays
     uint8_t* d_vectors_ = nullptr;

@@ -74,15 +74,20 @@ const uint8_t* get_list(const uint8_t* p, uint32_t* ids, size_t width, size_t n_
 
 } // namespace
 
-size_t Index::serialized_length() {
-    flush_staged();
-    std::lock_guard<std::mutex> g(mu_);
+// caller holds mu_
+size_t Index::serialized_length_locked() {
     if (pending_n_)
         build_pending(*this);
     size_t total = 136;
     for (size_t i = 0; i < n_; ++i)
         total += 10 + (4 + 6 * cfg_.M0) + (size_t)h_levels_[i] * (4 + 6 * cfg_.M) + stored_bytes_;
     return total;
+}
+
+size_t Index::serialized_length() {
+    flush_staged();
+    std::lock_guard<std::mutex> g(mu_);
+    return serialized_length_locked();
 }
 
 // The 136 bytes in front of the node tapes: dense head, serialized header, vector_size_bytes, node_count.  Caller holds mu_.
@@ -112,8 +117,9 @@ void Index::write_header(void* headerp) {
 }
 
 size_t Index::save_buffer(void* buffer, size_t length) {
-    const size_t need = serialized_length();
-    std::lock_guard<std::mutex> g(mu_);
+    flush_staged();
+    std::lock_guard<std::mutex> g(mu_); // length check and node loop under ONE hold: a concurrent add cannot grow n_ in between
+    const size_t need = serialized_length_locked();
     if (length < need)
         throw CudaError("save_buffer: buffer too small (see lb200_serialized_length)");
     const size_t M = cfg_.M, M0 = cfg_.M0;
@@ -216,30 +222,34 @@ void Index::load_buffer(const void* buffer, size_t length) {
             }
         }
     }
-    // commit
-    n_ = 0, pending_n_ = 0;
-    ensure_capacity(n ? n : 1);
-    upper_lists_ = 0;
-    alloc_upper(upper_adj.size() / M + 1);
-    if (n) {
-        LB_CUDA(cudaMemcpy(d_vectors_, rows.data(), rows.size(), cudaMemcpyHostToDevice));
-        LB_CUDA(cudaMemset(d_adj0_, 0xFF, capacity_ * M0 * 4));
-        LB_CUDA(cudaMemcpy(d_adj0_, adj0.data(), adj0.size() * 4, cudaMemcpyHostToDevice));
-        LB_CUDA(cudaMemset(d_upper_ref_, 0xFF, capacity_ * 4));
-        LB_CUDA(cudaMemcpy(d_upper_ref_, upper_ref.data(), upper_ref.size() * 4, cudaMemcpyHostToDevice));
-        if (!upper_adj.empty())
-            LB_CUDA(cudaMemcpy(d_upper_adj_, upper_adj.data(), upper_adj.size() * 4, cudaMemcpyHostToDevice));
-        LB_CUDA(cudaMemcpy(d_keys_, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice));
-    }
+    uint32_t pq_max_code = 0;
     if (cfg_.pq) { // codes written by other tools may use all 256 centroids: size the look-up tables accordingly
-        pq_max_code_ = 0;
         for (size_t i = 0; i < n; ++i)
             for (size_t s2 = 0; s2 < stored_bytes_; ++s2) {
                 const uint8_t c = rows[i * row_bytes_ + s2];
                 if (c >= cfg_.num_centroids)
                     throw CudaError("corrupted centroid id"); // lantern_storage.hpp:141
-                pq_max_code_ = std::max<uint32_t>(pq_max_code_, c);
+                pq_max_code = std::max<uint32_t>(pq_max_code, c);
             }
+    }
+    // commit (nothing below throws for a reason that depends on the file contents)
+    pq_max_code_ = pq_max_code;
+    n_ = 0, pending_n_ = 0;
+    ensure_capacity(n ? n : 1);
+    upper_lists_ = 0;
+    alloc_upper(upper_adj.size() / M + 1);
+    // everything beyond the loaded nodes / lists must read as empty (0xFF): a later insert with level > max_level exposes
+    // its still-unwritten upper lists to greedy() before build_insert_kernel has filled them
+    LB_CUDA(cudaMemset(d_adj0_, 0xFF, capacity_ * M0 * 4));
+    LB_CUDA(cudaMemset(d_upper_ref_, 0xFF, capacity_ * 4));
+    LB_CUDA(cudaMemset(d_upper_adj_, 0xFF, upper_lists_cap_ * M * 4));
+    if (n) {
+        LB_CUDA(cudaMemcpy(d_vectors_, rows.data(), rows.size(), cudaMemcpyHostToDevice));
+        LB_CUDA(cudaMemcpy(d_adj0_, adj0.data(), adj0.size() * 4, cudaMemcpyHostToDevice));
+        LB_CUDA(cudaMemcpy(d_upper_ref_, upper_ref.data(), upper_ref.size() * 4, cudaMemcpyHostToDevice));
+        if (!upper_adj.empty())
+            LB_CUDA(cudaMemcpy(d_upper_adj_, upper_adj.data(), upper_adj.size() * 4, cudaMemcpyHostToDevice));
+        LB_CUDA(cudaMemcpy(d_keys_, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice));
     }
     upper_lists_ = upper_adj.size() / M;
     h_levels_ = std::move(levels);

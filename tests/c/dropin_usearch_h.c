@@ -9,9 +9,18 @@
 
 #include "usearch.h"
 
+/* build.c:512-517 fills the retriever fields before usearch_init although they are never called on the build path */
+static void* fake_retriever(void* ctx, unsigned long long id) {
+    (void)ctx, (void)id;
+    abort(); /* the engine must never call back into page storage */
+}
+
 int main(void) {
     usearch_init_options_t opts;
     memset(&opts, 0, sizeof(opts));
+    opts.retriever_ctx = &opts;
+    opts.retriever = (usearch_node_retriever_t)fake_retriever;
+    opts.retriever_mut = (usearch_node_retriever_t)fake_retriever;
     opts.metric_kind = usearch_metric_l2sq_k;
     opts.quantization = usearch_scalar_f32_k;
     opts.dimensions = 3;

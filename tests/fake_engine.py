@@ -105,6 +105,9 @@ class Index:
     def build(self):
         pass
 
+    def last_build_stats(self):
+        return dict(vectors=0, computed_distances=0, algorithmic_bytes=0, device_ms=0.0)
+
     def set_option(self, name, value):
         pass
 

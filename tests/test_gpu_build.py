@@ -4,7 +4,7 @@ import os
 import numpy as np
 import pytest
 
-from util import build_port_index, recall, structured
+from util import build_port_index, graph_agreement, recall, structured
 
 pytestmark = pytest.mark.gpu
 
@@ -42,12 +42,11 @@ def test_exact_order_build_is_byte_identical(eng, port, metric, d, M, efc):
     gb, pb = g.save_buffer(), pidx.save_buffer()
     assert len(gb) == len(pb)
     if not np.array_equal(gb, pb):
-        # ties inside the candidate queue can reorder equal-distance expansions; demand near-identity
-        assert np.mean(gb == pb) > 0.995
+        # ties inside the candidate queue can reorder equal-distance expansions; demand near-identity OF THE GRAPH (vectors and
+        # keys, most of the file, match trivially): the share of (node, level) adjacency lists that are identical
+        assert graph_agreement(gb, pb, M, d * 4) > 0.99
 
 
-@pytest.mark.skipif(not os.environ.get("LB200_UNVALIDATED"),
-                    reason="written at the end of round 1 without GPU access: run once with LB200_UNVALIDATED=1, then un-gate")
 @pytest.mark.parametrize("metric,d,M,efc,batch", [("l2sq", 48, 8, 64, 64), ("cos", 32, 16, 128, 256)])
 def test_batched_build_follows_the_cpu_model(eng, port, metric, d, M, efc, batch):
     """The DEFAULT (batched, two-phase) build against its CPU specification, oracle ora_add_batch_engine: same batch
@@ -69,7 +68,9 @@ def test_batched_build_follows_the_cpu_model(eng, port, metric, d, M, efc, batch
     g.build()
     gb, pb = g.save_buffer(), p.save_buffer()
     assert len(gb) == len(pb)
-    assert np.mean(gb == pb) > 0.995
+    agree = graph_agreement(gb, pb, M, d * 4)
+    print("batched build vs its CPU model: %.4f of the adjacency lists identical" % agree)
+    assert np.array_equal(gb, pb) or agree > 0.99
 
 
 def test_batched_build_recall_matches_reference_graph(eng, port):

@@ -54,3 +54,37 @@ def recall(found, truth):
     for f, t in zip(found, truth):
         hits += len(set(f.tolist()) & set(t.tolist()))
     return hits / truth.size
+
+
+def adjacency_lists(buf, M, stored_bytes):
+    """Parse a usearch/lantern index file into {(node, level): tuple(neighbour ids)} plus the level array.
+    Vectors and keys are skipped: comparisons through this helper look at the graph only."""
+    b = np.asarray(buf, dtype=np.uint8).tobytes()
+    n = int(np.frombuffer(b, np.uint64, 1, 80)[0])
+    M0 = 2 * M
+    lists, levels = {}, np.zeros(n, np.int16)
+    p = 136
+    for i in range(n):
+        lvl = int(np.frombuffer(b, np.int16, 1, p + 8)[0])
+        levels[i] = lvl
+        p += 10
+        for l in range(lvl + 1):
+            width = M0 if l == 0 else M
+            cnt = int(np.frombuffer(b, np.uint32, 1, p)[0])
+            raw = np.frombuffer(b, np.uint8, 6 * width, p + 4).reshape(width, 6)[:cnt]
+            ids = raw[:, :4].copy().view(np.uint32)[:, 0]
+            lists[(i, l)] = tuple(int(x) for x in ids)
+            p += 4 + 6 * width
+        p += stored_bytes
+    assert p == len(b), (p, len(b))
+    return lists, levels
+
+
+def graph_agreement(buf_a, buf_b, M, stored_bytes):
+    """Fraction of (node, level) adjacency lists that are identical (same ids, same order) in two index files."""
+    la, lva = adjacency_lists(buf_a, M, stored_bytes)
+    lb, lvb = adjacency_lists(buf_b, M, stored_bytes)
+    assert np.array_equal(lva, lvb), "level draws differ"
+    assert la.keys() == lb.keys()
+    same = sum(1 for k in la if la[k] == lb[k])
+    return same / max(1, len(la))
