@@ -50,6 +50,7 @@ __device__ __forceinline__ void list_insert(float* ld, uint64_t* li, uint32_t& s
             ld[idx] = vd, li[idx] = vi;
         __syncwarp();
     }
+    __syncwarp(); // the position scan's reads are ordered before this write even when nothing was shifted (racecheck)
     if (lane == 0)
         ld[pos] = d, li[pos] = id;
     __syncwarp();

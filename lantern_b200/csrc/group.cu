@@ -1,0 +1,1171 @@
+// lantern_b200 -- one HNSW graph searched by G GPUs at once ("row-sharded group").
+//
+// The multi-GPU form of the hot path (index_gt::search -> search_for_one_ -> search_to_find_in_base_,
+// U/include/usearch/index.hpp:2680-2730, 3277-3316, 3400-3485).  SURVEY.md 8(e) shards the corpus by contiguous
+// row range with one INDEPENDENT graph per GPU and broadcasts every query to every shard; HNSW's cost barely depends on
+// N, so that multiplies the total work by G (measured in round 1: 2.7x at 8 GPUs, recall-matched).  Here the corpus is
+// still sharded by row range -- GPU r holds the vectors of rows [bounds[r], bounds[r+1]) and nothing else of the 3 KB/row
+// payload -- but there is ONE graph: the adjacency lists (4 B per link, 8 % of the corpus at d=768/M=32) are replicated,
+// every query is walked once, by one "owner" warp, in the reference's exact order, and each distance is evaluated on the
+// GPU that owns the row.  Total row traffic is that of the 1-GPU search, split G ways; the results are those of the 1-GPU
+// search on the same graph, id for id (same decision sequence, same fp32 reduction order).
+//
+// Mapping to the machine.  Every GPU runs the same persistent kernel with W resident warps; warp `slot` serves query
+// slot, slot+W, ... on EVERY GPU at once: on GPU (slot mod G) it is the query's owner (top list, visited bitmap, the
+// reference's decisions), on the others a helper that keeps the query in shared memory and evaluates the rows it holds.
+// Per expansion the owner sends each helper the ids of the unseen neighbours that live there and receives their
+// distances; messages are 8-byte words {payload, flag} written straight into the peer's HBM over NVLink (peer-mapped
+// memory; NCCL's "LL" idea: the flag travels with the data, so no fence is needed and one NVLink write latency is the
+// whole cost) and polled locally.  The final top-k of a query is stored into every GPU's result buffer by its owner (the
+// all-gather of SURVEY 8e, fused into the search epilogue); a last-warp-out flag exchange makes kernel completion imply
+// that all peers' results have landed.  No NCCL, no host synchronisation on the hot path.
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "../../include/lantern_b200.h"
+#include "group.h"
+#include "walk.cuh"
+
+namespace lb200 {
+
+namespace {
+
+constexpr uint32_t kMsgDone = 0xFFFFFFFFu;
+constexpr int kGroupThreads = 128; // 4 independent warps per CTA (no CTA-wide synchronisation anywhere)
+constexpr int kGroupWarps = kGroupThreads / 32;
+
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned long long pack_word(uint32_t payload, uint32_t flag) {
+    return ((unsigned long long)flag << 32) | payload;
+}
+// 16 bytes of a row that nobody caches on our side (queries live in the root's memory: peer addresses bypass our L2 and
+// a stale L1 line of the previous batch must not be served)
+__device__ __forceinline__ uint4 ld_nocache_u4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+struct GroupWarpLayout {
+    uint32_t q, top_d, top_i, cand_id, cand_d, cand_slot, loc, limbo, total;
+};
+__host__ __device__ inline GroupWarpLayout group_warp_layout(uint32_t row_bytes, uint32_t L, uint32_t cap) {
+    GroupWarpLayout l;
+    uint32_t o = 0;
+    l.q = o, o += (row_bytes + 15u) & ~15u;
+    l.top_d = o, o += 4 * L;
+    l.top_i = o, o += 4 * L;
+    l.cand_id = o, o += 4 * cap;
+    l.cand_d = o, o += 4 * cap;
+    l.cand_slot = o, o += (2 * cap + 3u) & ~3u;
+    l.loc = o, o += (cap + 3u) & ~3u;
+    l.limbo = o, o += 4 * kLimboCap;
+    l.total = (o + 15u) & ~15u;
+    return l;
+}
+
+// ---- one warp = one query slot -------------------------------------------------------------------------------------
+template <int DM, int SK, int NQ> struct GroupWarp {
+    const GroupLaunch& p;
+    int lane;
+    uint32_t slot, nchunks, cap;
+    uint4* qs;
+    float* top_d;
+    uint32_t* top_i;
+    uint32_t* cand_id;
+    float* cand_d;
+    uint16_t* cand_slot;
+    uint8_t* loc;
+    uint32_t* limbo;
+    float a2;
+    uint32_t seq;  // owner: messages sent by this slot in this launch
+    uint32_t last; // helper: flag of the last request seen
+    bool dead;
+    unsigned long long t0;
+    uint32_t st_dist, st_pops, st_hops, st_rounds, st_rows;
+    const uint8_t* rows; // local slice, indexed by (global id - lo)
+    uint32_t lo;
+
+    __device__ __forceinline__ explicit GroupWarp(const GroupLaunch& gp) : p(gp) {}
+
+    __device__ __forceinline__ bool timed_out() {
+        if (ld_sys_u32(p.err[p.me]) != 0u)
+            return true;
+        if (globaltimer_ns() - t0 > p.timeout_ns) {
+            for (uint32_t r = 0; r < p.G; ++r)
+                st_sys_u32(p.err[r], 1u + p.me);
+            return true;
+        }
+        return false;
+    }
+    // spin until the word carries `flag`; returns its payload
+    __device__ __forceinline__ uint32_t wait_word(const unsigned long long* addr, uint32_t flag) {
+        uint32_t spins = 0;
+        for (;;) {
+            const unsigned long long v = ld_sys_u64(addr);
+            if ((uint32_t)(v >> 32) == flag)
+                return (uint32_t)v;
+            if (dead)
+                return 0u;
+            if ((++spins & 2047u) == 0u && timed_out()) {
+                dead = true;
+                return 0u;
+            }
+        }
+    }
+
+    __device__ __forceinline__ void load_query(uint32_t q) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.queries + (size_t)q * p.query_stride);
+        float part = 0.f;
+        for (uint32_t c = lane; c < nchunks; c += 32) {
+            const uint4 v = ld_nocache_u4(src + c);
+            qs[c] = v;
+            part += query_norm_chunk<DM, SK>(v);
+        }
+        a2 = 0.f;
+        if constexpr (DM == DM_COS)
+            a2 = warp_sum(part);
+        __syncwarp();
+    }
+
+    // distance query -> one local row (all loads of the row are issued before the first use).  Lane layout and reduction order
+    // are those of RowEval::row_distance (walk.cuh), so the value is bit-identical to the 1-GPU kernel's.
+    __device__ __forceinline__ float dist1(uint32_t id) const {
+        const uint4* ra = reinterpret_cast<const uint4*>(rows + (size_t)(id - lo) * p.g.row_bytes);
+        uint4 va[NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            const uint32_t c = lane + 32 * i;
+            if (c < nchunks)
+                va[i] = __ldg(ra + c);
+        }
+        DistAcc<DM, SK> acc;
+        acc.reset();
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            const uint32_t c = lane + 32 * i;
+            if (c < nchunks)
+                accum_chunk<DM, SK>(acc, qs[c], va[i]);
+        }
+        return finish_distance<DM, SK>(acc, a2);
+    }
+    // two rows: narrow rows (<= 3 chunks per lane) keep both in flight; wide rows would spill, the many resident warps
+    // provide the memory-level parallelism instead
+    __device__ __forceinline__ void dist2(uint32_t idA, uint32_t idB, float& dA, float& dB) const {
+        if constexpr (NQ > 3) {
+            dA = dist1(idA);
+            asm volatile("" ::: "memory"); // one row's loads in flight per warp: keep ptxas from hoisting the second row's
+            dB = (idB == idA) ? dA : dist1(idB);
+            asm volatile("" ::: "memory");
+        } else {
+            const uint4* ra = reinterpret_cast<const uint4*>(rows + (size_t)(idA - lo) * p.g.row_bytes);
+            const uint4* rb = reinterpret_cast<const uint4*>(rows + (size_t)(idB - lo) * p.g.row_bytes);
+            uint4 va[NQ], vb[NQ];
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                const uint32_t c = lane + 32 * i;
+                if (c < nchunks)
+                    va[i] = __ldg(ra + c), vb[i] = __ldg(rb + c);
+            }
+            DistAcc<DM, SK> accA, accB;
+            accA.reset(), accB.reset();
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                const uint32_t c = lane + 32 * i;
+                if (c < nchunks) {
+                    const uint4 qv = qs[c];
+                    accum_chunk<DM, SK>(accA, qv, va[i]);
+                    accum_chunk<DM, SK>(accB, qv, vb[i]);
+                }
+            }
+            dA = finish_distance<DM, SK>(accA, a2);
+            dB = finish_distance<DM, SK>(accB, a2);
+        }
+    }
+
+    // ---- owner: distances query -> cand_id[0..n) into cand_d[0..n), each evaluated where the row lives -----------
+    __device__ __forceinline__ void eval_round(uint32_t n) {
+        const uint32_t G = p.G, me = p.me;
+        const uint32_t flag = p.flag_base + (++seq);
+        const uint32_t lt = (1u << lane) - 1u;
+        uint32_t cnt = 0; // lane d < G: ids addressed to rank d in this round
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t j = base + lane;
+            const bool valid = j < n;
+            const uint32_t id = valid ? cand_id[j] : 0u;
+            uint32_t dst = 0xFFu;
+            if (valid) {
+                dst = 0;
+                while (id >= p.bounds[dst + 1])
+                    ++dst;
+            }
+            uint32_t pos = 0;
+            for (uint32_t d = 0; d < G; ++d) {
+                const uint32_t m = __ballot_sync(0xffffffffu, dst == d);
+                const uint32_t c_d = __shfl_sync(0xffffffffu, cnt, d);
+                if (dst == d)
+                    pos = c_d + __popc(m & lt);
+                if ((uint32_t)lane == d)
+                    cnt += __popc(m);
+            }
+            if (valid) {
+                cand_slot[j] = (uint16_t)((dst << 8) | pos);
+                if (dst != me)
+                    st_sys_u64(p.req[dst] + (size_t)slot * (1 + cap) + 1 + pos, pack_word(id, flag));
+                else
+                    loc[pos] = (uint8_t)j;
+            }
+        }
+        if ((uint32_t)lane < G && (uint32_t)lane != me && cnt)
+            st_sys_u64(p.req[lane] + (size_t)slot * (1 + cap), pack_word(cnt, flag));
+        const uint32_t nloc = __shfl_sync(0xffffffffu, cnt, me);
+        __syncwarp();
+#pragma unroll 1
+        for (uint32_t t = 0; t < nloc; t += 2) {
+            const uint32_t jA = loc[t], jB = (t + 1 < nloc) ? loc[t + 1] : jA;
+            float dA, dB;
+            dist2(cand_id[jA], cand_id[jB], dA, dB);
+            if (lane == 0) {
+                cand_d[jA] = dA;
+                cand_d[jB] = dB;
+            }
+        }
+        st_rows += nloc;
+        const unsigned long long* inbox = p.resp[me] + (size_t)slot * G * cap;
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t j = base + lane;
+            if (j < n) {
+                const uint32_t s = cand_slot[j], dst = s >> 8, pos = s & 255u;
+                if (dst != me)
+                    cand_d[j] = __uint_as_float(wait_word(inbox + (size_t)dst * cap + pos, flag));
+            }
+        }
+        dead = __any_sync(0xffffffffu, dead);
+        st_rounds += 1;
+        __syncwarp();
+    }
+
+    // ---- helper: serve the owner's requests for rows that live here until it says DONE ------------------------------
+    __device__ __forceinline__ void run_helper(uint32_t owner) {
+        const unsigned long long* hdr = p.req[p.me] + (size_t)slot * (1 + cap);
+        unsigned long long* outbox = p.resp[owner] + ((size_t)slot * p.G + p.me) * cap;
+        for (;;) {
+            uint32_t n_d = 0, flag = 0;
+            if (lane == 0) {
+                uint32_t spins = 0;
+                for (;;) {
+                    const unsigned long long v = ld_sys_u64(hdr);
+                    flag = (uint32_t)(v >> 32), n_d = (uint32_t)v;
+                    const uint32_t ahead = flag - last;
+                    if (ahead != 0u && ahead < (1u << 20) && flag - p.flag_base < (1u << 20))
+                        break;
+                    if ((++spins & 2047u) == 0u && timed_out()) {
+                        dead = true;
+                        break;
+                    }
+                    __nanosleep(32);
+                }
+            }
+            dead = __any_sync(0xffffffffu, dead);
+            if (dead)
+                return;
+            n_d = __shfl_sync(0xffffffffu, n_d, 0);
+            flag = __shfl_sync(0xffffffffu, flag, 0);
+            last = flag;
+            if (n_d == kMsgDone)
+                return;
+#pragma unroll 1
+            for (uint32_t base = 0; base < n_d; base += 32) {
+                const uint32_t cnt = min(32u, n_d - base);
+                const uint32_t my_id = (uint32_t)lane < cnt ? wait_word(hdr + 1 + base + lane, flag) : 0u;
+                dead = __any_sync(0xffffffffu, dead);
+                if (dead)
+                    return;
+                float my_d = 0.f;
+#pragma unroll 1
+                for (uint32_t t = 0; t < cnt; t += 2) {
+                    const uint32_t a = __shfl_sync(0xffffffffu, my_id, t);
+                    const uint32_t b = __shfl_sync(0xffffffffu, my_id, (t + 1 < cnt) ? t + 1 : t);
+                    float dA, dB;
+                    dist2(a, b, dA, dB);
+                    if ((uint32_t)lane == t)
+                        my_d = dA;
+                    if ((uint32_t)lane == t + 1)
+                        my_d = dB;
+                }
+                if ((uint32_t)lane < cnt)
+                    st_sys_u64(outbox + base + lane, pack_word(__float_as_uint(my_d), flag));
+            }
+            st_rows += n_d;
+        }
+    }
+
+    // ---- owner: the reference's walk, one warp --------------------------------------------------------------------
+    __device__ __forceinline__ void greedy(uint32_t& cur, float& cur_d) {
+        for (int level = p.g.max_level; level > 0; --level) {
+            for (;;) {
+                const uint32_t* list = p.g.upper_adj + ((size_t)__ldg(p.g.upper_ref + cur) + (level - 1)) * p.g.M;
+                uint32_t n = 0;
+                for (uint32_t off = 0; off < p.g.M; off += 32) {
+                    const uint32_t id = (off + lane < p.g.M) ? __ldg(list + off + lane) : kNoNeighbor;
+                    const bool valid = id != kNoNeighbor;
+                    const uint32_t m = __ballot_sync(0xffffffffu, valid);
+                    if (valid)
+                        cand_id[n + __popc(m & ((1u << lane) - 1u))] = id;
+                    n += __popc(m);
+                }
+                __syncwarp();
+                if (n)
+                    eval_round(n);
+                if (dead)
+                    return;
+                float best = cur_d; // one pass of index.hpp:3304-3311 == first minimum below cur_d
+                int bi = -1;
+                for (uint32_t j = 0; j < n; ++j) {
+                    const float d = cand_d[j];
+                    if (d < best)
+                        best = d, bi = (int)j;
+                }
+                st_dist += n, st_hops += 1;
+                if (bi < 0)
+                    break;
+                cur = cand_id[bi], cur_d = best;
+                __syncwarp();
+            }
+        }
+    }
+
+    __device__ __forceinline__ uint32_t beam(uint32_t start, float start_d, uint32_t L, uint32_t* vis, uint32_t* touched) {
+        const uint32_t M0 = p.g.M0;
+        uint32_t size = 1, cursor = 0, ntouched = 1, limbo_n = 0;
+        float limbo_d = 0.f;
+        if (lane == 0) {
+            top_d[0] = start_d, top_i[0] = start;
+            atomicOr(&vis[start >> 5], 1u << (start & 31));
+            touched[0] = start >> 5;
+        }
+        st_dist += 1; // index.hpp:3436
+        __syncwarp();
+        for (;;) {
+            // pop the closest unexpanded entry (walk.cuh TopSmem::pop), or a tie waiting in limbo
+            uint32_t c = kNoNeighbor;
+            if (cursor < size) {
+                c = top_i[cursor];
+                __syncwarp();
+                if (lane == 0)
+                    top_i[cursor] = c | kExpandedBit;
+                __syncwarp();
+                uint32_t nxt = size;
+                for (uint32_t b = cursor + 1; b < size; b += 32) {
+                    const uint32_t e = b + lane;
+                    const bool un = e < size && !(top_i[e] & kExpandedBit);
+                    const uint32_t m = __ballot_sync(0xffffffffu, un);
+                    if (m) {
+                        nxt = b + __ffs(m) - 1;
+                        break;
+                    }
+                }
+                cursor = nxt;
+            } else if (limbo_n) {
+                c = limbo[--limbo_n];
+            }
+            if (c == kNoNeighbor)
+                break;
+            uint32_t n = 0;
+            const uint32_t* list = p.g.adj0 + (size_t)c * M0;
+            for (uint32_t off = 0; off < M0; off += 32) {
+                const uint32_t id = (off + lane < M0) ? __ldg(list + off + lane) : kNoNeighbor;
+                const bool valid = id != kNoNeighbor;
+                if (!__any_sync(0xffffffffu, valid))
+                    break;
+                const uint32_t peers = __match_any_sync(0xffffffffu, id);
+                const bool first = valid && ((uint32_t)(__ffs(peers) - 1) == (uint32_t)lane);
+                bool fresh = false;
+                if (first) {
+                    const uint32_t bit = 1u << (id & 31);
+                    fresh = !(atomicOr(&vis[id >> 5], bit) & bit);
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, fresh);
+                const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+                if (fresh) {
+                    cand_id[n + rank] = id;
+                    if (ntouched + rank < p.touched_cap)
+                        touched[ntouched + rank] = id >> 5;
+                }
+                n += __popc(m);
+                ntouched += __popc(m);
+            }
+            st_pops += 1;
+            __syncwarp();
+            if (n)
+                eval_round(n);
+            if (dead)
+                break;
+            st_dist += n;
+            // index.hpp:3470: accepted iff top.size() < L || d < radius; parallel pre-filter, then replay in stored order
+            for (uint32_t base = 0; base < n; base += 32) {
+                const uint32_t j = base + lane;
+                const float dj = j < n ? cand_d[j] : INFINITY;
+                float radius = top_d[size - 1];
+                uint32_t m = __ballot_sync(0xffffffffu, j < n && (size < L || dj < radius));
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float d = __shfl_sync(0xffffffffu, dj, b);
+                    if (size < L || d < radius) {
+                        const uint32_t id = cand_id[base + b];
+                        float ev_d;
+                        uint32_t ev_i;
+                        top_insert(top_d, top_i, size, cursor, L, d, id, lane, ev_d, ev_i);
+                        if ((p.g.flags & 2u) && lane == 0)
+                            prefetch_l2(p.g.adj0 + (size_t)id * M0);
+                        radius = top_d[size - 1];
+                        if (limbo_n && radius < limbo_d)
+                            limbo_n = 0;
+                        if (ev_i != kNoNeighbor && !(ev_i & kExpandedBit) && ev_d == radius && limbo_n < kLimboCap) {
+                            if (lane == 0)
+                                limbo[limbo_n] = ev_i;
+                            limbo_n++, limbo_d = radius;
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // un-visit only the words this walk touched
+        if (ntouched <= p.touched_cap) {
+            for (uint32_t i = lane; i < ntouched; i += 32)
+                vis[touched[i]] = 0u;
+        } else {
+            for (size_t i = lane; i < p.words_per_slot; i += 32)
+                vis[i] = 0u;
+        }
+        __syncwarp();
+        return size;
+    }
+
+    __device__ __forceinline__ void run_owner(uint32_t q) {
+        uint32_t* vis = p.vis + (size_t)(slot / p.G) * p.words_per_slot;
+        uint32_t* touched = p.touched + (size_t)(slot / p.G) * p.touched_cap;
+        uint32_t cur = p.g.entry;
+        if (lane == 0)
+            cand_id[0] = cur;
+        __syncwarp();
+        eval_round(1);
+        float cur_d = cand_d[0];
+        st_dist += 1;
+        __syncwarp();
+        uint32_t size = 0;
+        if (!dead)
+            greedy(cur, cur_d);
+        if (!dead)
+            size = beam(cur, cur_d, p.L, vis, touched);
+        // results -> every rank (the all-gather of SURVEY 8e, fused); top is ascending, shrink(k), keys
+        const uint32_t found = dead ? 0u : min(size, p.k);
+        for (uint32_t i = lane; i < p.k; i += 32) {
+            unsigned long long key = ~0ull;
+            float d = INFINITY;
+            if (i < found) {
+                key = __ldg(p.g.keys + (top_i[i] & kIdMask));
+                d = top_d[i];
+            }
+            for (uint32_t r = 0; r < p.G; ++r) {
+                p.res_keys[r][(size_t)q * p.k + i] = key;
+                p.res_dists[r][(size_t)q * p.k + i] = d;
+            }
+        }
+        if ((uint32_t)lane < p.G)
+            p.res_counts[lane][q] = found;
+        // release the helpers of this query
+        const uint32_t flag = p.flag_base + (++seq);
+        if ((uint32_t)lane < p.G && (uint32_t)lane != p.me)
+            st_sys_u64(p.req[lane] + (size_t)slot * (1 + cap), pack_word(kMsgDone, flag));
+        __syncwarp();
+    }
+};
+
+template <int DM, int SK, int NQ>
+__global__ void __launch_bounds__(kGroupThreads, 1) group_search_kernel(const __grid_constant__ GroupLaunch p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    GroupWarp<DM, SK, NQ> w(p);
+    w.lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    w.slot = blockIdx.x * kGroupWarps + warp;
+    w.cap = p.cap;
+    w.nchunks = p.g.row_bytes / 16;
+    const GroupWarpLayout lay = group_warp_layout(p.g.row_bytes, p.L, p.cap);
+    uint8_t* ws = smem_raw + (size_t)warp * lay.total;
+    w.qs = reinterpret_cast<uint4*>(ws + lay.q);
+    w.top_d = reinterpret_cast<float*>(ws + lay.top_d);
+    w.top_i = reinterpret_cast<uint32_t*>(ws + lay.top_i);
+    w.cand_id = reinterpret_cast<uint32_t*>(ws + lay.cand_id);
+    w.cand_d = reinterpret_cast<float*>(ws + lay.cand_d);
+    w.cand_slot = reinterpret_cast<uint16_t*>(ws + lay.cand_slot);
+    w.loc = ws + lay.loc;
+    w.limbo = reinterpret_cast<uint32_t*>(ws + lay.limbo);
+    w.seq = 0, w.last = p.flag_base, w.dead = false, w.a2 = 0.f;
+    w.st_dist = w.st_pops = w.st_hops = w.st_rounds = w.st_rows = 0;
+    w.rows = p.g.vectors, w.lo = p.bounds[p.me];
+    w.t0 = globaltimer_ns();
+
+    // the root's query staging buffer is complete when its kernel starts (stream order): tell everybody
+    if (p.me == p.root && w.slot == 0 && (uint32_t)w.lane < p.G)
+        st_sys_u64(p.qready[w.lane], (unsigned long long)p.epoch);
+    const uint32_t owner = w.slot % p.G; // W is a multiple of G: a slot keeps its owner for the whole launch
+    bool waited = (p.me == p.root);
+    for (uint32_t q = w.slot; q < p.nq; q += p.W) {
+        if (!waited) {
+            if (w.lane == 0) {
+                uint32_t spins = 0;
+                while (ld_sys_u64(p.qready[p.me]) != (unsigned long long)p.epoch) {
+                    if ((++spins & 2047u) == 0u && w.timed_out()) {
+                        w.dead = true;
+                        break;
+                    }
+                    __nanosleep(64);
+                }
+            }
+            w.dead = __any_sync(0xffffffffu, w.dead);
+            waited = true;
+        }
+        if (w.dead)
+            break;
+        w.load_query(q);
+        if (owner == p.me)
+            w.run_owner(q);
+        else
+            w.run_helper(owner);
+    }
+    // completion: results of this GPU's owners are visible system-wide before its done flag is
+    __threadfence_system();
+    __syncwarp();
+    bool last_warp = false;
+    if (w.lane == 0) {
+        atomicAdd(&p.counters[1], (unsigned long long)w.st_dist);
+        atomicAdd(&p.counters[2], (unsigned long long)w.st_pops);
+        atomicAdd(&p.counters[3], (unsigned long long)w.st_hops);
+        atomicAdd(&p.counters[4], (unsigned long long)w.st_rounds);
+        atomicAdd(&p.counters[5], (unsigned long long)w.st_rows);
+        __threadfence();
+        last_warp = atomicAdd(&p.counters[0], 1ull) == (unsigned long long)gridDim.x * kGroupWarps - 1ull;
+    }
+    last_warp = __shfl_sync(0xffffffffu, last_warp, 0);
+    if (last_warp) {
+        __threadfence_system();
+        if ((uint32_t)w.lane < p.G) {
+            st_sys_u64(p.done[w.lane] + p.me, (unsigned long long)p.epoch);
+            uint32_t spins = 0;
+            while (ld_sys_u64(p.done[p.me] + w.lane) != (unsigned long long)p.epoch) {
+                if ((++spins & 2047u) == 0u && w.timed_out())
+                    break;
+                __nanosleep(64);
+            }
+        }
+        __threadfence_system();
+    }
+}
+
+template <int DM, int SK, int NQ> void group_launch_one(const GroupLaunch& p, uint32_t grid, size_t smem, cudaStream_t stream) {
+    auto kern = group_search_kernel<DM, SK, NQ>;
+    LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kGroupThreads, smem, stream>>>(p);
+    LB_CUDA(cudaGetLastError());
+    count_launch();
+}
+template <int DM, int SK, int NQ> int group_occupancy_one(size_t smem) {
+    auto kern = group_search_kernel<DM, SK, NQ>;
+    LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks = 0;
+    LB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, kGroupThreads, smem));
+    return blocks;
+}
+
+__global__ void group_copy_results_kernel(const uint64_t* __restrict__ rk, const float* __restrict__ rd, const uint32_t* __restrict__ rc,
+                                          uint64_t* __restrict__ keys, float* __restrict__ dists, uint32_t* __restrict__ counts,
+                                          size_t nq, size_t k) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq * k) {
+        if (keys)
+            keys[i] = rk[i];
+        if (dists)
+            dists[i] = rd[i];
+    }
+    if (counts && i < nq)
+        counts[i] = rc[i];
+}
+
+} // namespace
+
+// =====================================================================================================================
+// host side
+// =====================================================================================================================
+
+struct PtrBlob { // how one device allocation is handed to the other ranks
+    cudaIpcMemHandle_t ipc;
+    void* raw;
+};
+
+struct GroupConfigBlob {
+    uint32_t valid;
+    int32_t metric_kind, scalar_kind;
+    uint64_t dims, M, M0, ef, n, upper_lists, row_bytes, vec_bytes;
+    uint32_t entry;
+    int32_t max_level;
+    uint32_t flags;
+    PtrBlob vectors, adj0, upper_ref, upper_adj, keys;
+};
+
+struct SlabLayout {
+    size_t req, resp, res_keys, res_dists, res_counts, done, qready, err, qbuf, total;
+};
+
+static SlabLayout slab_layout(uint32_t Wmax, uint32_t G, uint32_t cap, size_t res_cap, size_t max_batch, size_t qrow) {
+    SlabLayout s;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        const size_t at = o;
+        o += round_up(bytes, 256);
+        return at;
+    };
+    s.req = take((size_t)Wmax * (1 + cap) * 8);
+    s.resp = take((size_t)Wmax * G * cap * 8);
+    s.res_keys = take(res_cap * 8);
+    s.res_dists = take(res_cap * 4);
+    s.res_counts = take(max_batch * 4);
+    s.done = take(kGroupMax * 8);
+    s.qready = take(8);
+    s.err = take(4);
+    s.qbuf = take(max_batch * qrow);
+    s.total = o;
+    return s;
+}
+
+class GroupRank {
+  public:
+    int rank = 0, world = 1, device = 0;
+    bool local = false; // all ranks live in this process (peer pointers are used directly)
+    IndexConfig cfg;
+    int dist_mode = 0;
+    size_t n = 0, row_bytes = 0, vec_bytes = 0, upper_lists = 0;
+    uint32_t entry = 0, flags = 2;
+    int32_t max_level = -1;
+    uint32_t bounds[kGroupMax + 1] = {0};
+    // local copies
+    uint8_t* d_rows = nullptr;
+    uint32_t *d_adj0 = nullptr, *d_upper_ref = nullptr, *d_upper_adj = nullptr;
+    uint64_t* d_keys = nullptr;
+    // mailboxes
+    uint8_t* slab = nullptr;
+    uint8_t* peer_slab[kGroupMax] = {nullptr};
+    SlabLayout lay{};
+    uint32_t Wmax = 0, cap = 0;
+    size_t res_cap = 0, max_batch = 0;
+    // owner scratch
+    uint32_t *d_vis = nullptr, *d_touched = nullptr;
+    size_t words_per_slot = 0;
+    uint32_t touched_cap = 16384;
+    unsigned long long* d_counters = nullptr;
+    uint32_t epoch = 0;
+    std::map<uint32_t, uint32_t> W_for_L; // agreed resident warps per GPU for a beam width
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t last_nq = 0;
+    std::vector<void*> opened; // IPC mappings to close
+
+    ~GroupRank() {
+        cudaSetDevice(device);
+        for (void* p : opened)
+            cudaIpcCloseMemHandle(p);
+        cudaFree(d_rows), cudaFree(d_adj0), cudaFree(d_upper_ref), cudaFree(d_upper_adj), cudaFree(d_keys);
+        cudaFree(slab), cudaFree(d_vis), cudaFree(d_touched), cudaFree(d_counters);
+        if (ev0)
+            cudaEventDestroy(ev0);
+        if (ev1)
+            cudaEventDestroy(ev1);
+    }
+
+    PtrBlob export_ptr(void* p) const {
+        PtrBlob b;
+        memset(&b, 0, sizeof(b));
+        b.raw = p;
+        if (!local && p)
+            LB_CUDA(cudaIpcGetMemHandle(&b.ipc, p));
+        return b;
+    }
+    // a pointer of rank `src` usable on this rank's device; `keep` = stays mapped for the life of the group
+    void* import_ptr(const PtrBlob& b, int src, bool keep) {
+        if (!b.raw)
+            return nullptr;
+        if (local || src == rank)
+            return b.raw;
+        void* p = nullptr;
+        LB_CUDA(cudaIpcOpenMemHandle(&p, b.ipc, cudaIpcMemLazyEnablePeerAccess));
+        if (keep)
+            opened.push_back(p);
+        return p;
+    }
+    void release_ptr(void* p, int src) {
+        if (!local && src != rank && p)
+            LB_CUDA(cudaIpcCloseMemHandle(p));
+    }
+
+    // ---- distribute: phase A (root describes its index), B (everybody copies its share), C (map the peers' slabs) ----
+    GroupConfigBlob describe(Index* idx) {
+        GroupConfigBlob c;
+        memset(&c, 0, sizeof(c));
+        if (!idx)
+            return c;
+        idx->flush_staged();
+        std::lock_guard<std::mutex> g(idx->mu_);
+        if (idx->pending_n_)
+            build_pending(*idx);
+        if (idx->cfg_.pq)
+            throw CudaError("group: pq indexes are not supported");
+        if (idx->n_ == 0)
+            throw CudaError("group: the index is empty");
+        LB_CUDA(cudaDeviceSynchronize());
+        c.valid = 1;
+        c.metric_kind = idx->cfg_.metric_kind, c.scalar_kind = idx->cfg_.scalar_kind;
+        c.dims = idx->cfg_.dims, c.M = idx->cfg_.M, c.M0 = idx->cfg_.M0, c.ef = idx->cfg_.ef;
+        c.n = idx->n_, c.upper_lists = idx->upper_lists_, c.row_bytes = idx->row_bytes_, c.vec_bytes = idx->vec_bytes_;
+        c.entry = idx->entry_, c.max_level = idx->max_level_;
+        c.flags = idx->view().flags;
+        c.vectors = export_ptr(idx->d_vectors_), c.adj0 = export_ptr(idx->d_adj0_);
+        c.upper_ref = export_ptr(idx->d_upper_ref_), c.upper_adj = export_ptr(idx->d_upper_adj_);
+        c.keys = export_ptr(idx->d_keys_);
+        return c;
+    }
+
+    PtrBlob adopt(const GroupConfigBlob& c, int root, size_t max_batch_, size_t max_results) {
+        if (!c.valid)
+            throw CudaError("group: the root rank passed no index");
+        LB_CUDA(cudaSetDevice(device));
+        cfg = IndexConfig();
+        cfg.metric_kind = c.metric_kind, cfg.scalar_kind = c.scalar_kind;
+        cfg.dims = c.dims, cfg.M = c.M, cfg.M0 = c.M0, cfg.ef = c.ef;
+        dist_mode = distance_mode(cfg.metric_kind, cfg.scalar_kind);
+        n = c.n, row_bytes = c.row_bytes, vec_bytes = c.vec_bytes, upper_lists = c.upper_lists;
+        entry = c.entry, max_level = c.max_level, flags = c.flags;
+        if (cfg.M0 > 256)
+            throw CudaError("group: connectivity above 128 is not supported");
+        for (int r = 0; r <= world; ++r)
+            bounds[r] = (uint32_t)((n * (size_t)r) / (size_t)world); // contiguous row ranges
+        const size_t lo = bounds[rank], hi = bounds[rank + 1];
+        LB_CUDA(cudaMalloc(&d_rows, std::max<size_t>((hi - lo) * row_bytes, 16)));
+        LB_CUDA(cudaMalloc(&d_adj0, n * cfg.M0 * 4));
+        LB_CUDA(cudaMalloc(&d_upper_ref, n * 4));
+        LB_CUDA(cudaMalloc(&d_upper_adj, std::max<size_t>(upper_lists * cfg.M * 4, 16)));
+        LB_CUDA(cudaMalloc(&d_keys, n * 8));
+        auto fetch = [&](void* dst, const PtrBlob& b, size_t offset, size_t bytes) {
+            if (!bytes)
+                return;
+            uint8_t* src = (uint8_t*)import_ptr(b, root, false);
+            LB_CUDA(cudaMemcpy(dst, src + offset, bytes, cudaMemcpyDefault));
+            release_ptr(src, root);
+        };
+        fetch(d_rows, c.vectors, lo * row_bytes, (hi - lo) * row_bytes);
+        fetch(d_adj0, c.adj0, 0, n * cfg.M0 * 4);
+        fetch(d_upper_ref, c.upper_ref, 0, n * 4);
+        fetch(d_upper_adj, c.upper_adj, 0, upper_lists * cfg.M * 4);
+        fetch(d_keys, c.keys, 0, n * 8);
+        // mailboxes
+        int sms = 0;
+        LB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        cap = (uint32_t)cfg.M0;
+        Wmax = (uint32_t)sms * 8u * kGroupWarps; // upper bound of resident warps (8 CTAs per SM)
+        max_batch = max_batch_, res_cap = max_results;
+        lay = slab_layout(Wmax, (uint32_t)world, cap, res_cap, max_batch, row_bytes);
+        LB_CUDA(cudaMalloc(&slab, lay.total));
+        LB_CUDA(cudaMemset(slab, 0, lay.total));
+        // owner scratch: one visited bitmap per owned slot
+        words_per_slot = round_up((n + 31) / 32, 32);
+        const size_t owned = (Wmax + world - 1) / world;
+        LB_CUDA(cudaMalloc(&d_vis, owned * words_per_slot * 4));
+        LB_CUDA(cudaMemset(d_vis, 0, owned * words_per_slot * 4));
+        LB_CUDA(cudaMalloc(&d_touched, owned * (size_t)touched_cap * 4));
+        LB_CUDA(cudaMalloc(&d_counters, 8 * sizeof(unsigned long long)));
+        LB_CUDA(cudaMemset(d_counters, 0, 8 * sizeof(unsigned long long)));
+        LB_CUDA(cudaEventCreate(&ev0));
+        LB_CUDA(cudaEventCreate(&ev1));
+        LB_CUDA(cudaDeviceSynchronize());
+        return export_ptr(slab);
+    }
+
+    void map_peers(const PtrBlob* slabs) {
+        LB_CUDA(cudaSetDevice(device));
+        for (int r = 0; r < world; ++r)
+            peer_slab[r] = (uint8_t*)import_ptr(slabs[r], r, true);
+    }
+
+    int occupancy_for(uint32_t L) {
+        LB_CUDA(cudaSetDevice(device));
+        const size_t smem = (size_t)group_warp_layout((uint32_t)row_bytes, L, cap).total * kGroupWarps;
+        const int nq = pick_nq((uint32_t)row_bytes);
+        if (nq < 0)
+            throw CudaError("group: vectors wider than 8192 bytes are not supported");
+        int occ = 0;
+        dispatch_walk(dist_mode, cfg.scalar_kind, nq, [&](auto d, auto s, auto q) {
+            occ = group_occupancy_one<decltype(d)::value, decltype(s)::value, decltype(q)::value>(smem);
+        });
+        int sms = 0;
+        LB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        return occ * sms * kGroupWarps;
+    }
+
+    uint8_t* qbuf() const { return slab + lay.qbuf; }
+
+    // queries: only the root's are read.  Asynchronous on `stream`.
+    void launch(const void* d_queries, size_t nq, size_t stride, int kind, size_t k, uint32_t L, uint32_t W, int root,
+                uint64_t* d_out_keys, float* d_out_dists, uint32_t* d_out_counts, cudaStream_t stream) {
+        LB_CUDA(cudaSetDevice(device));
+        if (nq > max_batch || nq * k > res_cap)
+            throw CudaError("group: batch larger than the group was created for (max_batch / max_results)");
+        if (rank == root) {
+            if (!d_queries)
+                throw CudaError("group: the root rank must pass the queries");
+            launch_cast_rows(d_queries, stride, kind, qbuf(), row_bytes, cfg.scalar_kind, cfg.dims, nq, stream);
+        }
+        ++epoch;
+        if ((epoch & 0xFFFu) == 0u)
+            throw CudaError("group: flag space exhausted (re-create the group after 4095 searches)"); // see search_collective
+        GroupLaunch p;
+        memset(&p, 0, sizeof(p));
+        p.G = (uint32_t)world, p.me = (uint32_t)rank, p.W = W, p.cap = cap;
+        p.nq = (uint32_t)nq, p.k = (uint32_t)k, p.L = L;
+        p.flag_base = (epoch & 0xFFFu) << 20;
+        p.epoch = epoch, p.root = (uint32_t)root;
+        p.timeout_ns = 8ull * 1000ull * 1000ull * 1000ull;
+        p.g.vectors = d_rows, p.g.adj0 = d_adj0, p.g.upper_ref = d_upper_ref, p.g.upper_adj = d_upper_adj, p.g.keys = d_keys;
+        p.g.n = (uint32_t)n, p.g.row_bytes = (uint32_t)row_bytes, p.g.M = (uint32_t)cfg.M, p.g.M0 = (uint32_t)cfg.M0;
+        p.g.entry = entry, p.g.max_level = max_level, p.g.flags = flags, p.g.dims = (uint32_t)cfg.dims;
+        for (int r = 0; r <= world; ++r)
+            p.bounds[r] = bounds[r];
+        for (int r = world + 1; r <= kGroupMax; ++r)
+            p.bounds[r] = 0xFFFFFFFFu;
+        for (int r = 0; r < world; ++r) {
+            uint8_t* s = peer_slab[r];
+            p.req[r] = (unsigned long long*)(s + lay.req), p.resp[r] = (unsigned long long*)(s + lay.resp);
+            p.res_keys[r] = (uint64_t*)(s + lay.res_keys), p.res_dists[r] = (float*)(s + lay.res_dists);
+            p.res_counts[r] = (uint32_t*)(s + lay.res_counts);
+            p.done[r] = (unsigned long long*)(s + lay.done), p.qready[r] = (unsigned long long*)(s + lay.qready);
+            p.err[r] = (uint32_t*)(s + lay.err);
+        }
+        p.queries = peer_slab[root] + lay.qbuf, p.query_stride = (uint32_t)row_bytes;
+        p.vis = d_vis, p.touched = d_touched, p.words_per_slot = words_per_slot, p.touched_cap = touched_cap;
+        p.counters = d_counters;
+        LB_CUDA(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned long long), stream));
+        const size_t smem = (size_t)group_warp_layout((uint32_t)row_bytes, L, cap).total * kGroupWarps;
+        const uint32_t slots = (uint32_t)std::min<size_t>(W, round_up(nq, (size_t)world)); // W and nq rounded up are multiples of G
+        const uint32_t grid = (slots + kGroupWarps - 1) / kGroupWarps;
+        p.W = W;
+        const int nqc = pick_nq((uint32_t)row_bytes);
+        LB_CUDA(cudaEventRecord(ev0, stream));
+        dispatch_walk(dist_mode, cfg.scalar_kind, nqc, [&](auto d, auto s, auto q) {
+            group_launch_one<decltype(d)::value, decltype(s)::value, decltype(q)::value>(p, grid, smem, stream);
+        });
+        LB_CUDA(cudaEventRecord(ev1, stream));
+        if (d_out_keys || d_out_dists || d_out_counts) {
+            const size_t total = std::max(nq * k, nq);
+            group_copy_results_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+                (const uint64_t*)(slab + lay.res_keys), (const float*)(slab + lay.res_dists), (const uint32_t*)(slab + lay.res_counts),
+                d_out_keys, d_out_dists, d_out_counts, nq, k);
+            LB_CUDA(cudaGetLastError());
+            count_launch();
+        }
+        last_nq = (uint32_t)nq;
+    }
+
+    void check_error() {
+        uint32_t e = 0;
+        LB_CUDA(cudaMemcpy(&e, slab + lay.err, 4, cudaMemcpyDeviceToHost));
+        if (e)
+            throw CudaError("group: a rank timed out waiting for a peer (rank " + std::to_string(e - 1) + " gave up first)");
+    }
+};
+
+// ---- the handle behind lb200_group_t: one rank of a multi-process group, or all ranks of a single-process one --------
+struct Group {
+    std::vector<GroupRank*> ranks; // 1 entry (multi-process) or `world` entries (single process)
+    int world = 1, root = 0;
+    lb200_allgather_fn ag = nullptr;
+    void* ag_ctx = nullptr;
+    bool distributed = false;
+    std::mutex mu;
+    std::vector<cudaStream_t> streams; // single-process: one per device
+    ~Group() {
+        for (GroupRank* r : ranks)
+            delete r;
+        for (size_t i = 0; i < streams.size(); ++i)
+            if (streams[i])
+                cudaStreamDestroy(streams[i]);
+    }
+    bool local() const { return ranks.size() > 1 || world == 1; }
+
+    // every rank contributes `bytes`; everybody receives world * bytes
+    void exchange(const std::vector<std::vector<uint8_t>>& mine, std::vector<uint8_t>& all, size_t bytes) {
+        all.assign((size_t)world * bytes, 0);
+        if (ranks.size() == (size_t)world) {
+            for (int r = 0; r < world; ++r)
+                memcpy(all.data() + (size_t)r * bytes, mine[r].data(), bytes);
+        } else {
+            ag(ag_ctx, mine[0].data(), all.data(), bytes);
+        }
+    }
+};
+
+static uint32_t agree_W(Group& G, uint32_t L) {
+    GroupRank* r0 = G.ranks[0];
+    auto it = r0->W_for_L.find(L);
+    if (it != r0->W_for_L.end())
+        return it->second;
+    std::vector<std::vector<uint8_t>> mine(G.ranks.size(), std::vector<uint8_t>(4));
+    for (size_t i = 0; i < G.ranks.size(); ++i) {
+        uint32_t w = (uint32_t)G.ranks[i]->occupancy_for(L);
+        memcpy(mine[i].data(), &w, 4);
+    }
+    std::vector<uint8_t> all;
+    G.exchange(mine, all, 4);
+    uint32_t W = 0xFFFFFFFFu;
+    for (int r = 0; r < G.world; ++r) {
+        uint32_t w;
+        memcpy(&w, all.data() + 4 * r, 4);
+        W = std::min(W, w);
+    }
+    W = std::min(W, r0->Wmax);
+    W -= W % (uint32_t)(G.world * kGroupWarps); // whole CTAs, and a slot keeps its owner across waves
+    if (W == 0)
+        throw CudaError("group: the search kernel does not fit on an SM (ef too large for shared memory)");
+    for (GroupRank* r : G.ranks)
+        r->W_for_L[L] = W;
+    return W;
+}
+
+void group_distribute(Group& G, Index* root_index, int root, size_t max_batch, size_t max_results) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (G.distributed)
+        throw CudaError("group: already distributed");
+    if (root < 0 || root >= G.world)
+        throw CudaError("group: bad root rank");
+    const size_t nr = G.ranks.size();
+    // A: the root describes its index
+    std::vector<std::vector<uint8_t>> mine(nr, std::vector<uint8_t>(sizeof(GroupConfigBlob)));
+    for (size_t i = 0; i < nr; ++i) {
+        GroupRank* r = G.ranks[i];
+        LB_CUDA(cudaSetDevice(r->device));
+        GroupConfigBlob c = r->describe(r->rank == root ? root_index : nullptr);
+        memcpy(mine[i].data(), &c, sizeof(c));
+    }
+    std::vector<uint8_t> all;
+    G.exchange(mine, all, sizeof(GroupConfigBlob));
+    GroupConfigBlob cfg;
+    memcpy(&cfg, all.data() + (size_t)root * sizeof(GroupConfigBlob), sizeof(cfg));
+    // B: every rank copies its row range and the graph from the root, allocates its mailboxes
+    std::vector<std::vector<uint8_t>> slabs(nr, std::vector<uint8_t>(sizeof(PtrBlob)));
+    for (size_t i = 0; i < nr; ++i) {
+        PtrBlob b = G.ranks[i]->adopt(cfg, root, max_batch, max_results);
+        memcpy(slabs[i].data(), &b, sizeof(b));
+    }
+    G.exchange(slabs, all, sizeof(PtrBlob)); // also tells the root that everybody is done reading its index
+    // C: map the peers' mailboxes
+    for (size_t i = 0; i < nr; ++i)
+        G.ranks[i]->map_peers((const PtrBlob*)all.data());
+    std::vector<std::vector<uint8_t>> tick(nr, std::vector<uint8_t>(4, 0));
+    G.exchange(tick, all, 4); // nobody searches before everybody has mapped everybody
+    G.root = root;
+    G.distributed = true;
+}
+
+static uint32_t beam_width(const GroupRank& r, size_t k, size_t ef) {
+    size_t L = ef ? ef : r.cfg.ef;
+    if (L < k)
+        L = k; // index.hpp:2706
+    if (L > 4096)
+        throw CudaError("search: max(ef, count) > 4096 is not supported");
+    return (uint32_t)L;
+}
+
+void group_search_device(Group& G, const void* d_queries, size_t nq, size_t stride, int kind, size_t k, size_t ef,
+                         uint64_t* d_keys, float* d_dists, uint32_t* d_counts, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!G.distributed)
+        throw CudaError("group: lb200_group_distribute has not been called");
+    if (G.ranks.size() != 1)
+        throw CudaError("group: device-buffer search is the multi-process entry point; use lb200_group_search_batch");
+    if (!nq || !k)
+        return;
+    GroupRank* r = G.ranks[0];
+    const uint32_t L = beam_width(*r, k, ef);
+    const uint32_t W = agree_W(G, L);
+    r->launch(d_queries, nq, stride, kind, k, L, W, G.root, d_keys, d_dists, d_counts, stream);
+}
+
+// host buffers: queries are read on the root rank only; every rank receives the results
+void group_search_host(Group& G, const void* queries, size_t nq, size_t stride, int kind, size_t k, size_t ef, uint64_t* keys,
+                       float* dists, size_t* counts) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!G.distributed)
+        throw CudaError("group: lb200_group_distribute has not been called");
+    if (!nq || !k)
+        return;
+    const size_t nr = G.ranks.size();
+    GroupRank* r0 = G.ranks[0];
+    const uint32_t L = beam_width(*r0, k, ef);
+    const uint32_t W = agree_W(G, L);
+    const size_t in_bytes = scalar_row_bytes(kind, r0->cfg.dims);
+    if (G.streams.size() != nr) {
+        G.streams.assign(nr, nullptr);
+        for (size_t i = 0; i < nr; ++i) {
+            LB_CUDA(cudaSetDevice(G.ranks[i]->device));
+            LB_CUDA(cudaStreamCreateWithFlags(&G.streams[i], cudaStreamNonBlocking));
+        }
+    }
+    void* d_in = nullptr;
+    for (size_t i = 0; i < nr; ++i) {
+        GroupRank* r = G.ranks[i];
+        LB_CUDA(cudaSetDevice(r->device));
+        const void* dq = nullptr;
+        if (r->rank == G.root) {
+            if (!queries)
+                throw CudaError("group: the root rank must pass the queries");
+            LB_CUDA(cudaMallocAsync(&d_in, nq * in_bytes, G.streams[i]));
+            LB_CUDA(cudaMemcpy2DAsync(d_in, in_bytes, queries, stride, in_bytes, nq, cudaMemcpyHostToDevice, G.streams[i]));
+            dq = d_in;
+        }
+        r->launch(dq, nq, in_bytes, kind, k, L, W, G.root, nullptr, nullptr, nullptr, G.streams[i]);
+        if (r->rank == G.root)
+            LB_CUDA(cudaFreeAsync(d_in, G.streams[i]));
+    }
+    // results: from the first rank of this process (every rank holds all of them)
+    LB_CUDA(cudaSetDevice(r0->device));
+    cudaStream_t s0 = G.streams[0];
+    if (keys)
+        LB_CUDA(cudaMemcpyAsync(keys, r0->slab + r0->lay.res_keys, nq * k * 8, cudaMemcpyDeviceToHost, s0));
+    if (dists)
+        LB_CUDA(cudaMemcpyAsync(dists, r0->slab + r0->lay.res_dists, nq * k * 4, cudaMemcpyDeviceToHost, s0));
+    std::vector<uint32_t> c32;
+    if (counts) {
+        c32.resize(nq);
+        LB_CUDA(cudaMemcpyAsync(c32.data(), r0->slab + r0->lay.res_counts, nq * 4, cudaMemcpyDeviceToHost, s0));
+    }
+    for (size_t i = 0; i < nr; ++i) {
+        LB_CUDA(cudaSetDevice(G.ranks[i]->device));
+        LB_CUDA(cudaStreamSynchronize(G.streams[i]));
+    }
+    for (size_t i = 0; i < nr; ++i) {
+        LB_CUDA(cudaSetDevice(G.ranks[i]->device));
+        G.ranks[i]->check_error();
+    }
+    if (counts)
+        for (size_t i = 0; i < nq; ++i)
+            counts[i] = c32[i];
+    LB_CUDA(cudaSetDevice(r0->device));
+}
+
+void group_stats(Group& G, int which, GroupStats& out) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (which < 0 || (size_t)which >= G.ranks.size())
+        throw CudaError("group: no such local rank");
+    GroupRank* r = G.ranks[which];
+    LB_CUDA(cudaSetDevice(r->device));
+    LB_CUDA(cudaDeviceSynchronize());
+    r->check_error();
+    unsigned long long c[8] = {0};
+    LB_CUDA(cudaMemcpy(c, r->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+    memset(&out, 0, sizeof(out));
+    out.rank = r->rank, out.world = r->world;
+    out.queries = r->last_nq;
+    out.owner_computed_distances = c[1], out.owner_base_pops = c[2], out.owner_upper_hops = c[3], out.owner_rounds = c[4];
+    out.local_rows_evaluated = c[5];
+    out.local_row_bytes = c[5] * r->vec_bytes;
+    out.rows_held = r->bounds[r->rank + 1] - r->bounds[r->rank];
+    float ms = 0.f;
+    if (r->last_nq && cudaEventElapsedTime(&ms, r->ev0, r->ev1) == cudaSuccess)
+        out.kernel_ms = ms;
+    else
+        (void)cudaGetLastError();
+}
+
+Group* group_create_ipc(int rank, int world, lb200_allgather_fn ag, void* ctx) {
+    if (world < 1 || world > kGroupMax || rank < 0 || rank >= world)
+        throw CudaError("group: world size must be 1..8 and 0 <= rank < world");
+    if (world > 1 && !ag)
+        throw CudaError("group: an all-gather callback is required to bootstrap a multi-process group");
+    require_device();
+    Group* G = new Group();
+    G->world = world, G->ag = ag, G->ag_ctx = ctx;
+    GroupRank* r = new GroupRank();
+    r->rank = rank, r->world = world, r->local = (world == 1);
+    LB_CUDA(cudaGetDevice(&r->device));
+    G->ranks.push_back(r);
+    return G;
+}
+
+Group* group_create_local(const int* devices, int ndev) {
+    if (ndev < 1 || ndev > kGroupMax)
+        throw CudaError("group: 1..8 devices");
+    require_device();
+    int have = 0;
+    LB_CUDA(cudaGetDeviceCount(&have));
+    Group* G = new Group();
+    G->world = ndev;
+    try {
+        for (int i = 0; i < ndev; ++i) {
+            const int dev = devices ? devices[i] : i;
+            if (dev < 0 || dev >= have)
+                throw CudaError("group: no such CUDA device");
+            GroupRank* r = new GroupRank();
+            r->rank = i, r->world = ndev, r->local = true, r->device = dev;
+            G->ranks.push_back(r);
+        }
+        for (int i = 0; i < ndev; ++i) {
+            LB_CUDA(cudaSetDevice(G->ranks[i]->device));
+            for (int j = 0; j < ndev; ++j) {
+                if (i == j)
+                    continue;
+                int can = 0;
+                LB_CUDA(cudaDeviceCanAccessPeer(&can, G->ranks[i]->device, G->ranks[j]->device));
+                if (!can)
+                    throw CudaError("group: the devices cannot access each other's memory (no NVLink / P2P)");
+                cudaError_t e = cudaDeviceEnablePeerAccess(G->ranks[j]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    LB_CUDA(e);
+                (void)cudaGetLastError();
+            }
+        }
+    } catch (...) {
+        delete G;
+        throw;
+    }
+    return G;
+}
+
+void group_free(Group* G) { delete G; }
+int group_world(const Group& G) { return G.world; }
+int group_local_ranks(const Group& G) { return (int)G.ranks.size(); }
+
+} // namespace lb200

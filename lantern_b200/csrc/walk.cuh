@@ -128,6 +128,7 @@ __device__ __forceinline__ void top_insert(float* td, uint32_t* ti, uint32_t& si
             td[idx] = vd, ti[idx] = vi;
         __syncwarp();
     }
+    __syncwarp(); // the position scan's reads are ordered before this write even when nothing was shifted (racecheck)
     if (lane == 0)
         td[pos] = d, ti[pos] = id;
     __syncwarp();

@@ -47,15 +47,18 @@ def test_exact_order_build_is_byte_identical(eng, port, metric, d, M, efc):
         assert graph_agreement(gb, pb, M, d * 4) > 0.99
 
 
-@pytest.mark.parametrize("metric,d,M,efc,batch", [("l2sq", 48, 8, 64, 64), ("cos", 32, 16, 128, 256)])
-def test_batched_build_follows_the_cpu_model(eng, port, metric, d, M, efc, batch):
+@pytest.mark.parametrize("metric,d,M,efc,batch,lim,floor", [("l2sq", 16, 8, 64, 64, 300, 0.995), ("l2sq", 48, 8, 64, 64, 8, 0.95),
+                                                            ("cos", 32, 16, 128, 256, 8, 0.95)])
+def test_batched_build_follows_the_cpu_model(eng, port, metric, d, M, efc, batch, lim, floor):
     """The DEFAULT (batched, two-phase) build against its CPU specification, oracle ora_add_batch_engine: same batch
     schedule (build_batch / build_ratio), same phase-1 searches against the pre-batch graph, same stable request order in
-    phase 2 -> the same index file on integer-valued data (up to the tie order inside the candidate queue, as in the
-    sequential case above)."""
+    phase 2.  First case: integer coordinates in [-300, 300], d=16 -- every squared distance is an exact fp32 integer
+    (< 2^24) whatever the summation order, and exact ties are rare, so the two graphs must agree (almost) list for list.
+    The other two cases use small integers, where exact ties are everywhere: the engine pops equal-distance candidates in a
+    different order than the reference's binary heap, which perturbs a few per cent of the lists."""
     rng = np.random.default_rng(19)
     n = 3000
-    X = rng.integers(-8, 9, (n, d)).astype(np.float32)
+    X = rng.integers(-lim, lim + 1, (n, d)).astype(np.float32)
     keys = np.arange(1, n + 1, dtype=np.uint64)
     p = port.PortIndex(d, metric, "f32", M=M, efc=efc, ef=32)
     p.reserve(n)
@@ -69,8 +72,8 @@ def test_batched_build_follows_the_cpu_model(eng, port, metric, d, M, efc, batch
     gb, pb = g.save_buffer(), p.save_buffer()
     assert len(gb) == len(pb)
     agree = graph_agreement(gb, pb, M, d * 4)
-    print("batched build vs its CPU model: %.4f of the adjacency lists identical" % agree)
-    assert np.array_equal(gb, pb) or agree > 0.99
+    print("batched build vs its CPU model (%s, |x| <= %d): %.4f of the adjacency lists identical" % (metric, lim, agree))
+    assert np.array_equal(gb, pb) or agree >= floor
 
 
 def test_batched_build_recall_matches_reference_graph(eng, port):
