@@ -811,6 +811,208 @@ def run_ours(args, wl):
     if world > 1:
         dist.destroy_process_group()
 
+# --------------------------------------------------------------------------------------- our arm, N > 1: row-sharded group
+def run_group(args, wl):
+    """--gpus N > 1 (default mode "rows"): ONE graph over the whole corpus, vectors sharded by row range across the N GPUs,
+    every distance evaluated on the GPU that holds the row (lb200_group_*, csrc/group.cu).  Rank 0 generates the corpus and
+    builds the graph exactly as the 1-GPU run does; lb200_group_distribute hands every rank its row range and a copy of the
+    adjacency lists over NVLink.  Total work == the 1-GPU search; results == the 1-GPU results on the same graph (checked
+    in this run, `same_graph_as_1gpu`); recall therefore equals the 1-GPU recall at the same ef by construction."""
+    import torch
+    import torch.distributed as dist
+    from lantern_b200 import api
+
+    world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev, timeout=__import__("datetime").timedelta(minutes=30))
+    api.lib()
+    n, dim, k, ef, B = wl["n"], wl["dim"], wl["k"], wl["ef"], wl["batch"]
+    kind = wl.get("kind", "f32")
+    rowb = dim // 8 if kind == "b1" else dim * 4
+    gen_t = bits_torch if kind == "b1" else structured_torch
+    args.warmup = max(3, args.warmup)
+    nsteps = args.steps + args.warmup
+    pool = min(nsteps, args.query_pool)
+    stream = torch.cuda.current_stream()
+    nrec = min(B, 1024)
+
+    def allgather_bytes(send):  # bootstrap collective of the group (creation / distribution only)
+        t = torch.frombuffer(bytearray(send), dtype=torch.uint8).to(dev)
+        out = torch.empty((world, len(send)), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(out, t)
+        return out.cpu().numpy().tobytes()
+
+    grp = api.Group.ranked(rank, world, allgather_bytes)
+    idx, Q, truth, t_gen, t_build, build_work = None, None, None, 0.0, 0.0, [0, 0, 0.0]
+    if rank == 0:
+        t0 = time.perf_counter()
+        Q = gen_t(pool * B, dim, SEED_QUERY, dev)
+        X = gen_t(n, dim, SEED_CORPUS, dev)
+        torch.cuda.synchronize()
+        t_gen = time.perf_counter() - t0
+        idx = api.Index(dim, wl["metric"], kind, M=wl["M"], efc=wl["efc"], ef=ef)
+        idx.reserve(n)
+        t0 = time.perf_counter()
+        idx.add_batch_device(np.arange(1, n + 1, dtype=np.uint64), X.data_ptr(), n, rowb, kind)
+        idx.build()
+        torch.cuda.synchronize()
+        t_build = time.perf_counter() - t0
+        bst = idx.last_build_stats()
+        build_work = [bst["computed_distances"], bst["algorithmic_bytes"], bst["device_ms"]]
+        tk = torch.empty((nrec, k), dtype=torch.int64, device=dev)
+        td = torch.empty((nrec, k), dtype=torch.float32, device=dev)
+        api.exact_search_device(X.data_ptr(), n, rowb, Q.data_ptr(), nrec, rowb, k, tk.data_ptr(), td.data_ptr(), wl["metric"], kind,
+                                dim, stream.cuda_stream)
+        torch.cuda.synchronize()
+        truth = (tk + 1).cpu().numpy()
+        del X
+        torch.cuda.empty_cache()
+    t0 = time.perf_counter()
+    grp.distribute(idx, root=0, max_batch=B, max_results=B * k)
+    torch.cuda.synchronize()
+    t_dist = time.perf_counter() - t0
+
+    out_keys = torch.empty((B, k), dtype=torch.int64, device=dev)
+    out_dists = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_counts = torch.empty((B,), dtype=torch.int32, device=dev)
+
+    def step_device(s):
+        qp = Q[(s % pool) * B:((s % pool) + 1) * B].data_ptr() if rank == 0 else 0
+        grp.search_batch_device(qp, B, rowb, kind, k, ef, out_keys.data_ptr(), out_dists.data_ptr(), out_counts.data_ptr(),
+                                stream.cuda_stream)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    # same graph => same answer as the 1-GPU kernel (rank 0 still holds the whole index)
+    same, rec, one_gpu = None, None, None
+    step_device(0)
+    torch.cuda.synchronize()
+    if rank == 0:
+        k1 = torch.empty((B, k), dtype=torch.int64, device=dev)
+        d1 = torch.empty((B, k), dtype=torch.float32, device=dev)
+        idx.search_batch_device(Q.data_ptr(), B, rowb, kind, k, ef, k1.data_ptr(), d1.data_ptr(), 0, stream.cuda_stream)
+        torch.cuda.synchronize()
+        st1 = idx.last_stats()
+        same = {"identical_id_rows": float((k1 == out_keys).all(dim=1).float().mean().item()),
+                "bit_identical_distances": bool(torch.equal(d1.view(torch.int32), out_dists.view(torch.int32))),
+                "one_gpu_computed_distances": int(st1["computed_distances"])}
+        rec = recall_at_k(out_keys[:nrec].cpu().numpy(), truth)
+        # the 1-GPU kernel on the same graph, same queries, same box: the denominator of this run's own speed-up
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(3, min(20, args.steps))
+        for s_ in range(2):
+            idx.search_batch_device(Q[(s_ % pool) * B].data_ptr(), B, rowb, kind, k, ef, k1.data_ptr(), d1.data_ptr(), 0, stream.cuda_stream)
+        e0.record(stream)
+        for s_ in range(reps):
+            idx.search_batch_device(Q[(s_ % pool) * B].data_ptr(), B, rowb, kind, k, ef, k1.data_ptr(), d1.data_ptr(), 0, stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        one_gpu = {"value": reps * B / (e0.elapsed_time(e1) / 1e3), "unit": "queries/s", "recall_at_k": rec,
+                   "what": "lb200_search_batch_device on rank 0's unsharded copy of the same graph, %d steps" % reps}
+    for s in range(args.warmup):
+        step_device(s)
+    barrier()
+    launches0 = api.kernel_launches()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    ev[0].record(stream)
+    for s in range(args.warmup, nsteps):
+        step_device(s)
+    ev[1].record(stream)
+    barrier()
+    t = torch.tensor([ev[0].elapsed_time(ev[1])], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches = api.kernel_launches() - launches0
+    value = args.steps * B / (ms / 1e3)
+
+    # per-rank work of one step (the stats call synchronises): rows each GPU read, its kernel time
+    step_device(args.warmup)
+    st = grp.last_stats()
+    mine = torch.tensor([st["local_rows_evaluated"], st["local_row_bytes"], st["owner_computed_distances"], st["owner_base_pops"],
+                         st["owner_upper_hops"], st["owner_rounds"], st["kernel_ms"] * 1e6], dtype=torch.float64, device=dev)
+    allst = torch.empty((world, mine.numel()), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(allst, mine)
+    allst = allst.cpu().numpy()
+    extra = int(np.ceil(max(0.0, 600.0 - ms) / max(ms / args.steps, 1e-3)))
+    for s in range(extra):
+        step_device(args.warmup + s)
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["sampled_over"] = "timed steps + stats step + %d identical untimed steps" % extra
+
+    # e2e: ONE upload of the query batch from pinned host memory (rank 0), results back to the host on every rank
+    hq = hk = hd = hc = None
+    if rank == 0:
+        hq = torch.empty(Q.shape, dtype=Q.dtype).pin_memory()
+        hq.copy_(Q)
+    hk = torch.empty((B, k), dtype=torch.int64).pin_memory()
+    hd = torch.empty((B, k), dtype=torch.float32).pin_memory()
+    hc = torch.empty((B,), dtype=torch.int64).pin_memory()
+
+    def step_e2e(s):
+        grp.search_batch_raw(hq[(s % pool) * B].data_ptr() if rank == 0 else 0, B, rowb, kind, k, ef, hk.data_ptr(), hd.data_ptr(),
+                             hc.data_ptr())
+    for s in range(args.warmup):
+        step_e2e(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.warmup, nsteps):
+        step_e2e(s)
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt.item())
+    e2e = {"value": args.steps * B / dt, "unit": "queries/s", "h2d_bytes_per_step": B * rowb, "d2h_bytes_per_step": B * k * 12 + B * 4,
+           "ms_per_step": 1e3 * dt / args.steps,
+           "note": "rank 0 uploads the batch once from pinned host memory (the other GPUs read the queries over NVLink inside the "
+                   "kernel); every rank downloads the full top-k (bytes counted for rank 0)"}
+    if rank == 0:
+        peak, peak_src = peaks()
+        vec_bytes = rowb
+        alg = float(allst[:, 2].sum() * vec_bytes + allst[:, 3].sum() * (4 + 8 * wl["M"]) + allst[:, 4].sum() * (4 + 4 * wl["M"]) + B * vec_bytes)
+        kms = float(allst[:, 6].max() / 1e6)
+        per_rank = [{"rank": r, "rows_evaluated_per_query": float(allst[r, 0] / B), "row_gb_per_step": float(allst[r, 1] / 1e9),
+                     "kernel_ms": float(allst[r, 6] / 1e6), "local_hbm_frac": float(allst[r, 1] / (allst[r, 6] / 1e9) / 1e9 / peak)}
+                    for r in range(world)]
+        roofline = {"bound": "hbm", "achieved": alg / (kms / 1e3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                    "frac": alg / (kms / 1e3) / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src + " x %d GPUs" % world,
+                    "kernel": "group_search_kernel<%s,%s> on %d GPUs" % (wl["metric"], kind, world), "kernel_ms_per_step": kms,
+                    "algorithmic_bytes_per_step": alg, "dist_evals_per_query": float(allst[:, 2].sum() / B),
+                    "pops_per_query": float(allst[:, 3].sum() / B), "rounds_per_query": float(allst[:, 5].sum() / B),
+                    "timing": "one extra step after the timed region; kernel_ms = max over ranks of the search kernel's device time"}
+        line = {
+            "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8 (popcount)" if kind == "b1" else "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "corpus_rows": n, "rows_per_gpu": n // world, "ef": ef, "ef_per_shard": ef, "k": k,
+                       "search_order": "exact (reference order)", "batch": B,
+                       "parallelism": "one graph, vectors sharded by row range x%d (adjacency replicated), distances evaluated on the "
+                                      "owning GPU over NVLink peer memory, top-k all-gather fused into the kernel epilogue; no NCCL on "
+                                      "the search path" % world,
+                       "l2_policy": "inputs larger than L2: %.1f GB of rows per GPU gathered at random; %d distinct query batches cycled" % (
+                           n // world * rowb / 1e9, pool),
+                       "generator": ("64 random prototypes XOR 10%% bit flips, seeds %d/%d/%d" % (SEED_P, SEED_CORPUS, SEED_QUERY)) if kind == "b1" else
+                       "x = z P + %.2f eps, z~N(0,I_%d), seeds %d/%d/%d" % (NOISE, LATENT, SEED_P, SEED_CORPUS, SEED_QUERY)},
+            "recall_at_10": rec if k == 10 else None, "recall_at_k": rec, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": None, "cpu_baseline_note": "reported by the N=1 run", "parity": None,
+            "sharding": {"mode": "rows (one graph)", "same_graph_as_1gpu": same, "one_gpu_same_run": one_gpu, "per_rank": per_rank,
+                         "distribute_seconds": t_dist,
+                         "speedup_vs_one_gpu_same_run": value / one_gpu["value"] if one_gpu else None},
+            "pq": None,
+            "build": {"vectors_per_s": n / t_build, "seconds": t_build, "datagen_seconds": t_gen, "where": "rank 0 (one graph)",
+                      "dist_evals_per_vector": build_work[0] / max(1, n), "device_seconds": build_work[2] / 1e3},
+        }
+        print(json.dumps(line))
+    grp.close()
+    dist.destroy_process_group()
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -820,6 +1022,10 @@ def main():
     ap.add_argument("--query-pool", type=int, default=32, help="distinct query batches (cycled over the steps)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("LB200_WORKLOAD", "cfg3"), choices=sorted(WORKLOADS))
+    ap.add_argument("--shard-mode", default="rows", choices=["rows", "graphs"],
+                    help="--gpus > 1: 'rows' = ONE graph, vectors sharded by row range, distances evaluated on the owning GPU "
+                         "(lb200_group_*, results identical to 1 GPU); 'graphs' = round 1's independent graph per shard + NCCL "
+                         "all-gather + merge with a recall-matched per-shard ef")
     ap.add_argument("--shard-ef", type=int, default=0,
                     help="--gpus > 1: per-shard ef; 0 = recall-matched (smallest ef_s whose merged recall reaches the unsharded "
                          "1-GPU recall at the workload's ef), -1 = same ef as the workload")
@@ -840,6 +1046,8 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
+    elif int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.shard_mode == "rows" and not wl.get("pq") and DEVICE_TYPE == "cuda":
+        run_group(args, wl)
     else:
         run_ours(args, wl)
 

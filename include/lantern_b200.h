@@ -257,6 +257,52 @@ LB200_EXPORT void lb200_merge_shards_device(lb200_key_t const* d_keys, lb200_dis
                                             size_t nq, size_t count, lb200_key_t* d_out_keys,
                                             lb200_distance_t* d_out_dists, void* cuda_stream, lb200_error_t* error);
 
+/* ---- multi-GPU: one graph searched by G GPUs ("row-sharded group", csrc/group.cu) ------------------------------------
+ * The corpus is sharded by contiguous row range: GPU r holds the vectors of rows [n*r/G, n*(r+1)/G) only.
+ * The graph itself (adjacency lists, 4 B per link) is replicated, each query is walked ONCE in the reference's order, and
+ * every distance is evaluated on the GPU that holds the row, over NVLink peer memory -- total work equals the 1-GPU
+ * search, and so do the results (id for id on the same graph).  Two ways to form a group:
+ *   lb200_group_create        one process per GPU (torchrun / MPI style); `allgather` is the caller's bootstrap collective
+ *                             (every rank passes `bytes_per_rank` bytes, everybody receives world * bytes_per_rank, rank
+ *                             order); it is used at creation/distribution time only, never on the search path;
+ *   lb200_group_create_local  one process driving n devices (what a Lantern indexing/search server would do).
+ * lb200_group_distribute: the root rank passes a built (or loaded) index that lives on ITS device; every rank copies its
+ * row range and the graph from it over NVLink.  The root index is not modified and may be freed afterwards.  Collective.
+ * lb200_group_search_batch*: collective; only the root's queries are read (other ranks may pass NULL); EVERY rank receives
+ * the full result (the final all-gather is fused into the kernel's epilogue: owners store their top-k into every rank). */
+typedef void* lb200_group_t;
+typedef void (*lb200_allgather_fn)(void* ctx, void const* send, void* recv, size_t bytes_per_rank);
+typedef struct lb200_group_stats_t {
+    int rank, world;
+    uint64_t queries;                  /* of the last search batch */
+    uint64_t owner_computed_distances; /* distance evaluations REQUESTED by the queries this rank owns (sum over ranks ==
+                                          usearch's computed_distances of the same batch on the same graph) */
+    uint64_t owner_base_pops, owner_upper_hops, owner_rounds;
+    uint64_t local_rows_evaluated; /* rows of THIS rank's slice read and measured (its share of everybody's work) */
+    uint64_t local_row_bytes;      /* local_rows_evaluated * bytes per stored vector */
+    uint64_t rows_held;
+    double kernel_ms; /* device time of this rank's search kernel (CUDA events on its stream) */
+} lb200_group_stats_t;
+LB200_EXPORT lb200_group_t lb200_group_create(int rank, int world, lb200_allgather_fn allgather, void* allgather_ctx,
+                                              lb200_error_t* error);
+LB200_EXPORT lb200_group_t lb200_group_create_local(int const* devices, int n_devices, lb200_error_t* error);
+LB200_EXPORT void lb200_group_free(lb200_group_t, lb200_error_t* error);
+/* max_batch: largest nq of a search; max_results: largest nq * count (sizes the peer-mapped staging buffers). */
+LB200_EXPORT void lb200_group_distribute(lb200_group_t, lb200_index_t root_index, int root, size_t max_batch,
+                                         size_t max_results, lb200_error_t* error);
+/* host buffers in and out (host<->device copies included); counts may be NULL */
+LB200_EXPORT void lb200_group_search_batch(lb200_group_t, void const* queries, size_t nq, size_t stride,
+                                           lb200_scalar_kind_t query_kind, size_t count, size_t ef, lb200_key_t* keys,
+                                           lb200_distance_t* distances, size_t* counts, lb200_error_t* error);
+/* multi-process groups: device buffers of the calling rank, asynchronous on `cuda_stream`; when the stream reaches the
+ * end of this call's work, the results of ALL ranks' queries are in d_keys / d_distances / d_counts of this rank */
+LB200_EXPORT void lb200_group_search_batch_device(lb200_group_t, void const* d_queries, size_t nq, size_t stride,
+                                                  lb200_scalar_kind_t query_kind, size_t count, size_t ef,
+                                                  lb200_key_t* d_keys, lb200_distance_t* d_distances, uint32_t* d_counts,
+                                                  void* cuda_stream, lb200_error_t* error);
+/* local_rank: 0 for a multi-process group; 0..n_devices-1 for a single-process one.  Synchronises that device. */
+LB200_EXPORT void lb200_group_last_stats(lb200_group_t, int local_rank, lb200_group_stats_t* stats, lb200_error_t* error);
+
 /* ---- engine info ------------------------------------------------------------------------------- */
 LB200_EXPORT int lb200_device_count(void);
 LB200_EXPORT char const* lb200_version(void);

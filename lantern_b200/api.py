@@ -62,6 +62,14 @@ class BuildStats(C.Structure):
                 ("device_ms", C.c_double)]
 
 
+class GroupStats(C.Structure):
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("queries", C.c_uint64), ("owner_computed_distances", C.c_uint64),
+                ("owner_base_pops", C.c_uint64), ("owner_upper_hops", C.c_uint64), ("owner_rounds", C.c_uint64),
+                ("local_rows_evaluated", C.c_uint64), ("local_row_bytes", C.c_uint64), ("rows_held", C.c_uint64),
+                ("kernel_ms", C.c_double)]
+
+
+ALLGATHER_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
 ERRP = C.POINTER(C.c_char_p)
 
 # name -> (restype, argtypes); the same table drives the symbol-export test
@@ -124,6 +132,15 @@ SIGNATURES = {
                                         C.c_size_t, C.c_uint64, C.c_void_p, C.c_void_p, ERRP]),
     "lb200_merge_shards_device": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p,
                                          C.c_void_p, C.c_void_p, ERRP]),
+    "lb200_group_create": (C.c_void_p, [C.c_int, C.c_int, ALLGATHER_FN, C.c_void_p, ERRP]),
+    "lb200_group_create_local": (C.c_void_p, [C.c_void_p, C.c_int, ERRP]),
+    "lb200_group_free": (None, [C.c_void_p, ERRP]),
+    "lb200_group_distribute": (None, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, ERRP]),
+    "lb200_group_search_batch": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, ERRP]),
+    "lb200_group_search_batch_device": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, ERRP]),
+    "lb200_group_last_stats": (None, [C.c_void_p, C.c_int, C.POINTER(GroupStats), ERRP]),
     "lb200_device_count": (C.c_int, []),
     "lb200_version": (C.c_char_p, []),
     "lb200_kernel_launches": (C.c_uint64, []),
@@ -285,6 +302,82 @@ class Index:
 
     def load(self, path):
         self._call("lb200_load", path.encode())
+
+
+class Group:
+    """One graph searched by several GPUs (include/lantern_b200.h, "row-sharded group").
+
+    Group.local(devices)            one process driving len(devices) devices
+    Group.ranked(rank, world, ag)   one process per GPU; `ag(send: bytes) -> bytes` is the caller's all-gather
+                                    (concatenation of every rank's `send`, rank order), used for bootstrap only
+    """
+
+    def __init__(self, handle, world, keep=None):
+        self.h, self.world, self._keep = handle, world, keep
+
+    @classmethod
+    def local(cls, devices):
+        arr = (C.c_int * len(devices))(*devices)
+        err = C.c_char_p()
+        h = lib().lb200_group_create_local(arr, len(devices), C.byref(err))
+        _check(err)
+        return cls(h, len(devices))
+
+    @classmethod
+    def ranked(cls, rank, world, allgather):
+        def _ag(ctx, send, recv, nbytes):
+            out = allgather(C.string_at(send, nbytes))
+            assert len(out) == nbytes * world, (len(out), nbytes, world)
+            C.memmove(recv, out, len(out))
+        cb = ALLGATHER_FN(_ag)
+        err = C.c_char_p()
+        h = lib().lb200_group_create(rank, world, cb, None, C.byref(err))
+        _check(err)
+        return cls(h, world, keep=cb)
+
+    def close(self):
+        if getattr(self, "h", None):
+            err = C.c_char_p()
+            lib().lb200_group_free(self.h, C.byref(err))
+            self.h = None
+
+    __del__ = close
+
+    def _call(self, name, *args):
+        err = C.c_char_p()
+        r = getattr(lib(), name)(self.h, *args, C.byref(err))
+        _check(err)
+        return r
+
+    def distribute(self, index, root=0, max_batch=8192, max_results=0):
+        self._call("lb200_group_distribute", index.h if index is not None else None, root, max_batch, max_results)
+
+    def search_batch(self, queries, k, ef=0, nq=None, dim_bytes=None, kind=None):
+        """Host buffers.  Non-root ranks of a multi-process group pass queries=None with nq / dim_bytes / kind."""
+        if queries is not None:
+            queries = np.ascontiguousarray(queries)
+            nq, stride, kind_id = len(queries), queries.strides[0], Index._kind(queries)
+        else:
+            stride, kind_id = dim_bytes, SCALAR[kind]
+        keys = np.zeros((nq, k), np.uint64)
+        dists = np.zeros((nq, k), np.float32)
+        counts = np.zeros(nq, np.uint64)
+        self._call("lb200_group_search_batch", _ptr(queries), nq, stride, kind_id, k, ef, _ptr(keys), _ptr(dists), _ptr(counts))
+        return keys, dists, counts
+
+    def search_batch_raw(self, q_ptr, nq, stride, kind, k, ef, keys_ptr, dists_ptr, counts_ptr):
+        self._call("lb200_group_search_batch", C.c_void_p(q_ptr) if q_ptr else None, nq, stride, SCALAR[kind], k, ef,
+                   C.c_void_p(keys_ptr), C.c_void_p(dists_ptr), C.c_void_p(counts_ptr) if counts_ptr else None)
+
+    def search_batch_device(self, q_dptr, nq, stride, kind, k, ef, keys_dptr, dists_dptr, counts_dptr=0, stream=0):
+        self._call("lb200_group_search_batch_device", C.c_void_p(q_dptr) if q_dptr else None, nq, stride, SCALAR[kind], k, ef,
+                   C.c_void_p(keys_dptr) if keys_dptr else None, C.c_void_p(dists_dptr) if dists_dptr else None,
+                   C.c_void_p(counts_dptr) if counts_dptr else None, C.c_void_p(stream) if stream else None)
+
+    def last_stats(self, local_rank=0):
+        s = GroupStats()
+        self._call("lb200_group_last_stats", local_rank, C.byref(s))
+        return {f: getattr(s, f) for f, _ in GroupStats._fields_}
 
 
 def _static(name, *args):

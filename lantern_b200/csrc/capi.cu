@@ -16,6 +16,7 @@
 #include "../../include/lantern_b200.h"
 #include "distance.cuh"
 #include "engine.h"
+#include "group.h"
 
 using namespace lb200;
 
@@ -635,6 +636,64 @@ LB200_EXPORT void lb200_merge_shards_device(lb200_key_t const* d_keys, lb200_dis
     guarded(error, [&] {
         require_device();
         launch_merge_shards(d_keys, d_dists, shards, nq, count, d_out_keys, d_out_dists, (cudaStream_t)cuda_stream);
+    });
+}
+
+// ---- row-sharded multi-GPU group (group.cu) ---------------------------------------------------------------------
+static Group* as_group(lb200_group_t h) {
+    if (!h)
+        throw CudaError("null group handle");
+    return reinterpret_cast<Group*>(h);
+}
+LB200_EXPORT lb200_group_t lb200_group_create(int rank, int world, lb200_allgather_fn allgather, void* allgather_ctx,
+                                              lb200_error_t* error) {
+    lb200_group_t r = nullptr;
+    guarded(error, [&] { r = group_create_ipc(rank, world, allgather, allgather_ctx); });
+    return r;
+}
+LB200_EXPORT lb200_group_t lb200_group_create_local(int const* devices, int n_devices, lb200_error_t* error) {
+    lb200_group_t r = nullptr;
+    guarded(error, [&] { r = group_create_local(devices, n_devices); });
+    return r;
+}
+LB200_EXPORT void lb200_group_free(lb200_group_t h, lb200_error_t* error) {
+    guarded(error, [&] { group_free(reinterpret_cast<Group*>(h)); });
+}
+LB200_EXPORT void lb200_group_distribute(lb200_group_t h, lb200_index_t root_index, int root, size_t max_batch, size_t max_results,
+                                         lb200_error_t* error) {
+    guarded(error, [&] {
+        group_distribute(*as_group(h), reinterpret_cast<Index*>(root_index), root, max_batch ? max_batch : 8192,
+                         max_results ? max_results : (max_batch ? max_batch : 8192) * 128);
+    });
+}
+LB200_EXPORT void lb200_group_search_batch(lb200_group_t h, void const* queries, size_t nq, size_t stride,
+                                           lb200_scalar_kind_t kind, size_t count, size_t ef, lb200_key_t* keys,
+                                           lb200_distance_t* distances, size_t* counts, lb200_error_t* error) {
+    guarded(error, [&] { group_search_host(*as_group(h), queries, nq, stride, kind, count, ef, keys, distances, counts); });
+}
+LB200_EXPORT void lb200_group_search_batch_device(lb200_group_t h, void const* d_queries, size_t nq, size_t stride,
+                                                  lb200_scalar_kind_t kind, size_t count, size_t ef, lb200_key_t* d_keys,
+                                                  lb200_distance_t* d_distances, uint32_t* d_counts, void* cuda_stream,
+                                                  lb200_error_t* error) {
+    guarded(error, [&] {
+        group_search_device(*as_group(h), d_queries, nq, stride, kind, count, ef, d_keys, d_distances, d_counts,
+                            (cudaStream_t)cuda_stream);
+    });
+}
+LB200_EXPORT void lb200_group_last_stats(lb200_group_t h, int local_rank, lb200_group_stats_t* stats, lb200_error_t* error) {
+    guarded(error, [&] {
+        if (!stats)
+            throw CudaError("null stats pointer");
+        GroupStats s;
+        group_stats(*as_group(h), local_rank, s);
+        stats->rank = s.rank, stats->world = s.world;
+        stats->queries = s.queries;
+        stats->owner_computed_distances = s.owner_computed_distances;
+        stats->owner_base_pops = s.owner_base_pops, stats->owner_upper_hops = s.owner_upper_hops;
+        stats->owner_rounds = s.owner_rounds;
+        stats->local_rows_evaluated = s.local_rows_evaluated, stats->local_row_bytes = s.local_row_bytes;
+        stats->rows_held = s.rows_held;
+        stats->kernel_ms = s.kernel_ms;
     });
 }
 

@@ -35,7 +35,6 @@ namespace lb200 {
 
 namespace {
 
-constexpr uint32_t kMsgDone = 0xFFFFFFFFu;
 constexpr int kGroupThreads = 128; // 4 independent warps per CTA (no CTA-wide synchronisation anywhere)
 constexpr int kGroupWarps = kGroupThreads / 32;
 
@@ -90,30 +89,37 @@ __host__ __device__ inline GroupWarpLayout group_warp_layout(uint32_t row_bytes,
 }
 
 // ---- one warp = one query slot -------------------------------------------------------------------------------------
+// Header payloads of the owner -> helper mailbox: a count (1..cap) announces that many ids; kMsgStart | q opens query q
+// (the helper loads it into shared memory); kMsgExit ends the launch for this slot.
+constexpr uint32_t kMsgStart = 0x80000000u;
+constexpr uint32_t kMsgExit = 0xFFFFFFFFu;
+
 template <int DM, int SK, int NQ> struct GroupWarp {
     const GroupLaunch& p;
     int lane;
-    uint32_t slot, nchunks, cap;
-    uint4* qs;
-    float* top_d;
-    uint32_t* top_i;
-    uint32_t* cand_id;
-    float* cand_d;
-    uint16_t* cand_slot;
-    uint8_t* loc;
-    uint32_t* limbo;
+    uint32_t slot, nchunks;
+    uint8_t* ws; // this warp's shared memory
     float a2;
     uint32_t seq;  // owner: messages sent by this slot in this launch
-    uint32_t last; // helper: flag of the last request seen
-    bool dead;
+    uint32_t last; // helper: flag of the last header seen
+    bool dead, waited;
     unsigned long long t0;
     uint32_t st_dist, st_pops, st_hops, st_rounds, st_rows;
-    const uint8_t* rows; // local slice, indexed by (global id - lo)
-    uint32_t lo;
 
     __device__ __forceinline__ explicit GroupWarp(const GroupLaunch& gp) : p(gp) {}
 
-    __device__ __forceinline__ bool timed_out() {
+    // shared-memory arrays are addressed from one base (fewer live registers than eight pointers)
+    __device__ __forceinline__ GroupWarpLayout lay() const { return group_warp_layout(p.g.row_bytes, p.L, p.cap); }
+    __device__ __forceinline__ uint4* qs() const { return reinterpret_cast<uint4*>(ws); }
+    __device__ __forceinline__ float* top_d() const { return reinterpret_cast<float*>(ws + lay().top_d); }
+    __device__ __forceinline__ uint32_t* top_i() const { return reinterpret_cast<uint32_t*>(ws + lay().top_i); }
+    __device__ __forceinline__ uint32_t* cand_id() const { return reinterpret_cast<uint32_t*>(ws + lay().cand_id); }
+    __device__ __forceinline__ float* cand_d() const { return reinterpret_cast<float*>(ws + lay().cand_d); }
+    __device__ __forceinline__ uint16_t* cand_slot() const { return reinterpret_cast<uint16_t*>(ws + lay().cand_slot); }
+    __device__ __forceinline__ uint8_t* loc() const { return ws + lay().loc; }
+    __device__ __forceinline__ uint32_t* limbo() const { return reinterpret_cast<uint32_t*>(ws + lay().limbo); }
+
+    __device__ __noinline__ bool timed_out() {
         if (ld_sys_u32(p.err[p.me]) != 0u)
             return true;
         if (globaltimer_ns() - t0 > p.timeout_ns) {
@@ -139,12 +145,31 @@ template <int DM, int SK, int NQ> struct GroupWarp {
         }
     }
 
+    // non-root ranks read the queries from the root's staging buffer once the root's kernel has announced them
+    __device__ __forceinline__ void wait_queries() {
+        if (waited)
+            return;
+        if (lane == 0) {
+            uint32_t spins = 0;
+            while (ld_sys_u64(p.qready[p.me]) != (unsigned long long)p.epoch) {
+                if ((++spins & 2047u) == 0u && timed_out()) {
+                    dead = true;
+                    break;
+                }
+                __nanosleep(64);
+            }
+        }
+        dead = __any_sync(0xffffffffu, dead);
+        waited = true;
+    }
+
     __device__ __forceinline__ void load_query(uint32_t q) {
+        wait_queries();
         const uint4* src = reinterpret_cast<const uint4*>(p.queries + (size_t)q * p.query_stride);
         float part = 0.f;
         for (uint32_t c = lane; c < nchunks; c += 32) {
             const uint4 v = ld_nocache_u4(src + c);
-            qs[c] = v;
+            qs()[c] = v;
             part += query_norm_chunk<DM, SK>(v);
         }
         a2 = 0.f;
@@ -156,7 +181,7 @@ template <int DM, int SK, int NQ> struct GroupWarp {
     // distance query -> one local row (all loads of the row are issued before the first use).  Lane layout and reduction order
     // are those of RowEval::row_distance (walk.cuh), so the value is bit-identical to the 1-GPU kernel's.
     __device__ __forceinline__ float dist1(uint32_t id) const {
-        const uint4* ra = reinterpret_cast<const uint4*>(rows + (size_t)(id - lo) * p.g.row_bytes);
+        const uint4* ra = reinterpret_cast<const uint4*>(p.g.vectors + (size_t)(id - p.bounds[p.me]) * p.g.row_bytes);
         uint4 va[NQ];
 #pragma unroll
         for (int i = 0; i < NQ; ++i) {
@@ -166,58 +191,27 @@ template <int DM, int SK, int NQ> struct GroupWarp {
         }
         DistAcc<DM, SK> acc;
         acc.reset();
+        const uint4* q4 = qs();
 #pragma unroll
         for (int i = 0; i < NQ; ++i) {
             const uint32_t c = lane + 32 * i;
             if (c < nchunks)
-                accum_chunk<DM, SK>(acc, qs[c], va[i]);
+                accum_chunk<DM, SK>(acc, q4[c], va[i]);
         }
         return finish_distance<DM, SK>(acc, a2);
-    }
-    // two rows: narrow rows (<= 3 chunks per lane) keep both in flight; wide rows would spill, the many resident warps
-    // provide the memory-level parallelism instead
-    __device__ __forceinline__ void dist2(uint32_t idA, uint32_t idB, float& dA, float& dB) const {
-        if constexpr (NQ > 3) {
-            dA = dist1(idA);
-            asm volatile("" ::: "memory"); // one row's loads in flight per warp: keep ptxas from hoisting the second row's
-            dB = (idB == idA) ? dA : dist1(idB);
-            asm volatile("" ::: "memory");
-        } else {
-            const uint4* ra = reinterpret_cast<const uint4*>(rows + (size_t)(idA - lo) * p.g.row_bytes);
-            const uint4* rb = reinterpret_cast<const uint4*>(rows + (size_t)(idB - lo) * p.g.row_bytes);
-            uint4 va[NQ], vb[NQ];
-#pragma unroll
-            for (int i = 0; i < NQ; ++i) {
-                const uint32_t c = lane + 32 * i;
-                if (c < nchunks)
-                    va[i] = __ldg(ra + c), vb[i] = __ldg(rb + c);
-            }
-            DistAcc<DM, SK> accA, accB;
-            accA.reset(), accB.reset();
-#pragma unroll
-            for (int i = 0; i < NQ; ++i) {
-                const uint32_t c = lane + 32 * i;
-                if (c < nchunks) {
-                    const uint4 qv = qs[c];
-                    accum_chunk<DM, SK>(accA, qv, va[i]);
-                    accum_chunk<DM, SK>(accB, qv, vb[i]);
-                }
-            }
-            dA = finish_distance<DM, SK>(accA, a2);
-            dB = finish_distance<DM, SK>(accB, a2);
-        }
     }
 
     // ---- owner: distances query -> cand_id[0..n) into cand_d[0..n), each evaluated where the row lives -----------
     __device__ __forceinline__ void eval_round(uint32_t n) {
-        const uint32_t G = p.G, me = p.me;
+        const uint32_t G = p.G, me = p.me, cap = p.cap;
         const uint32_t flag = p.flag_base + (++seq);
         const uint32_t lt = (1u << lane) - 1u;
         uint32_t cnt = 0; // lane d < G: ids addressed to rank d in this round
+#pragma unroll 1
         for (uint32_t base = 0; base < n; base += 32) {
             const uint32_t j = base + lane;
             const bool valid = j < n;
-            const uint32_t id = valid ? cand_id[j] : 0u;
+            const uint32_t id = valid ? cand_id()[j] : 0u;
             uint32_t dst = 0xFFu;
             if (valid) {
                 dst = 0;
@@ -225,6 +219,7 @@ template <int DM, int SK, int NQ> struct GroupWarp {
                     ++dst;
             }
             uint32_t pos = 0;
+#pragma unroll 1
             for (uint32_t d = 0; d < G; ++d) {
                 const uint32_t m = __ballot_sync(0xffffffffu, dst == d);
                 const uint32_t c_d = __shfl_sync(0xffffffffu, cnt, d);
@@ -234,11 +229,11 @@ template <int DM, int SK, int NQ> struct GroupWarp {
                     cnt += __popc(m);
             }
             if (valid) {
-                cand_slot[j] = (uint16_t)((dst << 8) | pos);
+                cand_slot()[j] = (uint16_t)((dst << 8) | pos);
                 if (dst != me)
                     st_sys_u64(p.req[dst] + (size_t)slot * (1 + cap) + 1 + pos, pack_word(id, flag));
                 else
-                    loc[pos] = (uint8_t)j;
+                    loc()[pos] = (uint8_t)j;
             }
         }
         if ((uint32_t)lane < G && (uint32_t)lane != me && cnt)
@@ -246,23 +241,21 @@ template <int DM, int SK, int NQ> struct GroupWarp {
         const uint32_t nloc = __shfl_sync(0xffffffffu, cnt, me);
         __syncwarp();
 #pragma unroll 1
-        for (uint32_t t = 0; t < nloc; t += 2) {
-            const uint32_t jA = loc[t], jB = (t + 1 < nloc) ? loc[t + 1] : jA;
-            float dA, dB;
-            dist2(cand_id[jA], cand_id[jB], dA, dB);
-            if (lane == 0) {
-                cand_d[jA] = dA;
-                cand_d[jB] = dB;
-            }
+        for (uint32_t t = 0; t < nloc; ++t) {
+            const uint32_t j = loc()[t];
+            const float d = dist1(cand_id()[j]);
+            if (lane == 0)
+                cand_d()[j] = d;
         }
         st_rows += nloc;
         const unsigned long long* inbox = p.resp[me] + (size_t)slot * G * cap;
+#pragma unroll 1
         for (uint32_t base = 0; base < n; base += 32) {
             const uint32_t j = base + lane;
             if (j < n) {
-                const uint32_t s = cand_slot[j], dst = s >> 8, pos = s & 255u;
+                const uint32_t s = cand_slot()[j], dst = s >> 8, pos = s & 255u;
                 if (dst != me)
-                    cand_d[j] = __uint_as_float(wait_word(inbox + (size_t)dst * cap + pos, flag));
+                    cand_d()[j] = __uint_as_float(wait_word(inbox + (size_t)dst * cap + pos, flag));
             }
         }
         dead = __any_sync(0xffffffffu, dead);
@@ -270,10 +263,12 @@ template <int DM, int SK, int NQ> struct GroupWarp {
         __syncwarp();
     }
 
-    // ---- helper: serve the owner's requests for rows that live here until it says DONE ------------------------------
+    // ---- helper: follow the owner of this slot: START q / requests for rows that live here / EXIT -----------------------
     __device__ __forceinline__ void run_helper(uint32_t owner) {
+        const uint32_t cap = p.cap;
         const unsigned long long* hdr = p.req[p.me] + (size_t)slot * (1 + cap);
         unsigned long long* outbox = p.resp[owner] + ((size_t)slot * p.G + p.me) * cap;
+#pragma unroll 1
         for (;;) {
             uint32_t n_d = 0, flag = 0;
             if (lane == 0) {
@@ -297,8 +292,14 @@ template <int DM, int SK, int NQ> struct GroupWarp {
             n_d = __shfl_sync(0xffffffffu, n_d, 0);
             flag = __shfl_sync(0xffffffffu, flag, 0);
             last = flag;
-            if (n_d == kMsgDone)
+            if (n_d == kMsgExit)
                 return;
+            if (n_d & kMsgStart) {
+                load_query(n_d & ~kMsgStart);
+                if (dead)
+                    return;
+                continue;
+            }
 #pragma unroll 1
             for (uint32_t base = 0; base < n_d; base += 32) {
                 const uint32_t cnt = min(32u, n_d - base);
@@ -308,15 +309,10 @@ template <int DM, int SK, int NQ> struct GroupWarp {
                     return;
                 float my_d = 0.f;
 #pragma unroll 1
-                for (uint32_t t = 0; t < cnt; t += 2) {
-                    const uint32_t a = __shfl_sync(0xffffffffu, my_id, t);
-                    const uint32_t b = __shfl_sync(0xffffffffu, my_id, (t + 1 < cnt) ? t + 1 : t);
-                    float dA, dB;
-                    dist2(a, b, dA, dB);
+                for (uint32_t t = 0; t < cnt; ++t) {
+                    const float d = dist1(__shfl_sync(0xffffffffu, my_id, t));
                     if ((uint32_t)lane == t)
-                        my_d = dA;
-                    if ((uint32_t)lane == t + 1)
-                        my_d = dB;
+                        my_d = d;
                 }
                 if ((uint32_t)lane < cnt)
                     st_sys_u64(outbox + base + lane, pack_word(__float_as_uint(my_d), flag));
@@ -325,138 +321,165 @@ template <int DM, int SK, int NQ> struct GroupWarp {
         }
     }
 
-    // ---- owner: the reference's walk, one warp --------------------------------------------------------------------
-    __device__ __forceinline__ void greedy(uint32_t& cur, float& cur_d) {
-        for (int level = p.g.max_level; level > 0; --level) {
-            for (;;) {
+    __device__ __forceinline__ void tell_helpers(uint32_t payload) {
+        const uint32_t flag = p.flag_base + (++seq);
+        if ((uint32_t)lane < p.G && (uint32_t)lane != p.me)
+            st_sys_u64(p.req[lane] + (size_t)slot * (1 + p.cap), pack_word(payload, flag));
+    }
+
+    // ---- owner: the reference's walk of ONE query by one warp.  A single produce -> evaluate -> consume loop serves the entry
+    // point, the greedy descent (search_for_one_, index.hpp:3277-3316) and the base-layer beam (search_to_find_in_base_,
+    // :3400-3485), so that eval_round is instantiated once. -------------------------------------------------------------
+    __device__ __forceinline__ void run_owner(uint32_t q) {
+        const uint32_t M0 = p.g.M0, L = p.L;
+        uint32_t* vis = p.vis + (size_t)(slot / p.G) * p.words_per_slot;
+        uint32_t* touched = p.touched + (size_t)(slot / p.G) * p.touched_cap;
+        tell_helpers(kMsgStart | q);
+        load_query(q);
+        int level = -1; // -1: measuring the entry point; >= 1: greedy on that level; 0: beam on the base layer
+        uint32_t cur = p.g.entry;
+        float cur_d = 0.f;
+        uint32_t size = 0, cursor = 0, ntouched = 0, limbo_n = 0;
+        float limbo_d = 0.f;
+#pragma unroll 1
+        while (!dead) {
+            // ---- produce the ids to measure ----
+            uint32_t n = 0;
+            if (level < 0) {
+                if (lane == 0)
+                    cand_id()[0] = cur;
+                n = 1;
+            } else if (level > 0) {
                 const uint32_t* list = p.g.upper_adj + ((size_t)__ldg(p.g.upper_ref + cur) + (level - 1)) * p.g.M;
-                uint32_t n = 0;
                 for (uint32_t off = 0; off < p.g.M; off += 32) {
                     const uint32_t id = (off + lane < p.g.M) ? __ldg(list + off + lane) : kNoNeighbor;
                     const bool valid = id != kNoNeighbor;
                     const uint32_t m = __ballot_sync(0xffffffffu, valid);
                     if (valid)
-                        cand_id[n + __popc(m & ((1u << lane) - 1u))] = id;
+                        cand_id()[n + __popc(m & ((1u << lane) - 1u))] = id;
                     n += __popc(m);
                 }
-                __syncwarp();
-                if (n)
-                    eval_round(n);
-                if (dead)
-                    return;
-                float best = cur_d; // one pass of index.hpp:3304-3311 == first minimum below cur_d
-                int bi = -1;
-                for (uint32_t j = 0; j < n; ++j) {
-                    const float d = cand_d[j];
-                    if (d < best)
-                        best = d, bi = (int)j;
-                }
-                st_dist += n, st_hops += 1;
-                if (bi < 0)
-                    break;
-                cur = cand_id[bi], cur_d = best;
-                __syncwarp();
-            }
-        }
-    }
-
-    __device__ __forceinline__ uint32_t beam(uint32_t start, float start_d, uint32_t L, uint32_t* vis, uint32_t* touched) {
-        const uint32_t M0 = p.g.M0;
-        uint32_t size = 1, cursor = 0, ntouched = 1, limbo_n = 0;
-        float limbo_d = 0.f;
-        if (lane == 0) {
-            top_d[0] = start_d, top_i[0] = start;
-            atomicOr(&vis[start >> 5], 1u << (start & 31));
-            touched[0] = start >> 5;
-        }
-        st_dist += 1; // index.hpp:3436
-        __syncwarp();
-        for (;;) {
-            // pop the closest unexpanded entry (walk.cuh TopSmem::pop), or a tie waiting in limbo
-            uint32_t c = kNoNeighbor;
-            if (cursor < size) {
-                c = top_i[cursor];
-                __syncwarp();
-                if (lane == 0)
-                    top_i[cursor] = c | kExpandedBit;
-                __syncwarp();
-                uint32_t nxt = size;
-                for (uint32_t b = cursor + 1; b < size; b += 32) {
-                    const uint32_t e = b + lane;
-                    const bool un = e < size && !(top_i[e] & kExpandedBit);
-                    const uint32_t m = __ballot_sync(0xffffffffu, un);
-                    if (m) {
-                        nxt = b + __ffs(m) - 1;
-                        break;
+                st_hops += 1;
+            } else {
+                // pop the closest unexpanded entry (walk.cuh TopSmem::pop), or a tie waiting in limbo
+                uint32_t c = kNoNeighbor;
+                uint32_t* ti = top_i();
+                if (cursor < size) {
+                    c = ti[cursor];
+                    __syncwarp();
+                    if (lane == 0)
+                        ti[cursor] = c | kExpandedBit;
+                    __syncwarp();
+                    uint32_t nxt = size;
+                    for (uint32_t b = cursor + 1; b < size; b += 32) {
+                        const uint32_t e = b + lane;
+                        const bool un = e < size && !(ti[e] & kExpandedBit);
+                        const uint32_t m = __ballot_sync(0xffffffffu, un);
+                        if (m) {
+                            nxt = b + __ffs(m) - 1;
+                            break;
+                        }
                     }
+                    cursor = nxt;
+                } else if (limbo_n) {
+                    c = limbo()[--limbo_n];
                 }
-                cursor = nxt;
-            } else if (limbo_n) {
-                c = limbo[--limbo_n];
+                if (c == kNoNeighbor)
+                    break; // the beam is exhausted: index.hpp:3445 / queue empty
+                const uint32_t* list = p.g.adj0 + (size_t)c * M0;
+                for (uint32_t off = 0; off < M0; off += 32) {
+                    const uint32_t id = (off + lane < M0) ? __ldg(list + off + lane) : kNoNeighbor;
+                    const bool valid = id != kNoNeighbor;
+                    if (!__any_sync(0xffffffffu, valid))
+                        break;
+                    // duplicate ids inside one list are legal in reference graphs (refine_ padding, index.hpp:3554-3558)
+                    const uint32_t peers = __match_any_sync(0xffffffffu, id);
+                    const bool first = valid && ((uint32_t)(__ffs(peers) - 1) == (uint32_t)lane);
+                    bool fresh = false;
+                    if (first) {
+                        const uint32_t bit = 1u << (id & 31);
+                        fresh = !(atomicOr(&vis[id >> 5], bit) & bit);
+                    }
+                    const uint32_t m = __ballot_sync(0xffffffffu, fresh);
+                    const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+                    if (fresh) {
+                        cand_id()[n + rank] = id;
+                        if (ntouched + rank < p.touched_cap)
+                            touched[ntouched + rank] = id >> 5;
+                    }
+                    n += __popc(m);
+                    ntouched += __popc(m);
+                }
+                st_pops += 1;
             }
-            if (c == kNoNeighbor)
-                break;
-            uint32_t n = 0;
-            const uint32_t* list = p.g.adj0 + (size_t)c * M0;
-            for (uint32_t off = 0; off < M0; off += 32) {
-                const uint32_t id = (off + lane < M0) ? __ldg(list + off + lane) : kNoNeighbor;
-                const bool valid = id != kNoNeighbor;
-                if (!__any_sync(0xffffffffu, valid))
-                    break;
-                const uint32_t peers = __match_any_sync(0xffffffffu, id);
-                const bool first = valid && ((uint32_t)(__ffs(peers) - 1) == (uint32_t)lane);
-                bool fresh = false;
-                if (first) {
-                    const uint32_t bit = 1u << (id & 31);
-                    fresh = !(atomicOr(&vis[id >> 5], bit) & bit);
-                }
-                const uint32_t m = __ballot_sync(0xffffffffu, fresh);
-                const uint32_t rank = __popc(m & ((1u << lane) - 1u));
-                if (fresh) {
-                    cand_id[n + rank] = id;
-                    if (ntouched + rank < p.touched_cap)
-                        touched[ntouched + rank] = id >> 5;
-                }
-                n += __popc(m);
-                ntouched += __popc(m);
-            }
-            st_pops += 1;
             __syncwarp();
+            // ---- evaluate: every id on the GPU that holds its row ----
             if (n)
                 eval_round(n);
             if (dead)
                 break;
             st_dist += n;
-            // index.hpp:3470: accepted iff top.size() < L || d < radius; parallel pre-filter, then replay in stored order
-            for (uint32_t base = 0; base < n; base += 32) {
-                const uint32_t j = base + lane;
-                const float dj = j < n ? cand_d[j] : INFINITY;
-                float radius = top_d[size - 1];
-                uint32_t m = __ballot_sync(0xffffffffu, j < n && (size < L || dj < radius));
-                while (m) {
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    const float d = __shfl_sync(0xffffffffu, dj, b);
-                    if (size < L || d < radius) {
-                        const uint32_t id = cand_id[base + b];
-                        float ev_d;
-                        uint32_t ev_i;
-                        top_insert(top_d, top_i, size, cursor, L, d, id, lane, ev_d, ev_i);
-                        if ((p.g.flags & 2u) && lane == 0)
-                            prefetch_l2(p.g.adj0 + (size_t)id * M0);
-                        radius = top_d[size - 1];
-                        if (limbo_n && radius < limbo_d)
-                            limbo_n = 0;
-                        if (ev_i != kNoNeighbor && !(ev_i & kExpandedBit) && ev_d == radius && limbo_n < kLimboCap) {
-                            if (lane == 0)
-                                limbo[limbo_n] = ev_i;
-                            limbo_n++, limbo_d = radius;
-                            __syncwarp();
+            // ---- consume ----
+            if (level < 0) {
+                cur_d = cand_d()[0];
+                level = p.g.max_level;
+            } else if (level > 0) {
+                float best = cur_d; // one pass of index.hpp:3304-3311 == first minimum below cur_d
+                int bi = -1;
+                for (uint32_t j = 0; j < n; ++j) {
+                    const float d = cand_d()[j];
+                    if (d < best)
+                        best = d, bi = (int)j;
+                }
+                if (bi >= 0)
+                    cur = cand_id()[bi], cur_d = best;
+                else
+                    --level;
+                __syncwarp();
+            } else {
+                // index.hpp:3470: accepted iff top.size() < L || d < radius; parallel pre-filter, then replay in stored order
+                float* td = top_d();
+                uint32_t* ti = top_i();
+                for (uint32_t base = 0; base < n; base += 32) {
+                    const uint32_t j = base + lane;
+                    const float dj = j < n ? cand_d()[j] : INFINITY;
+                    float radius = td[size - 1];
+                    uint32_t m = __ballot_sync(0xffffffffu, j < n && (size < L || dj < radius));
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float d = __shfl_sync(0xffffffffu, dj, b);
+                        if (size < L || d < radius) {
+                            const uint32_t id = cand_id()[base + b];
+                            float ev_d;
+                            uint32_t ev_i;
+                            top_insert(td, ti, size, cursor, L, d, id, lane, ev_d, ev_i);
+                            if ((p.g.flags & 2u) && lane == 0)
+                                prefetch_l2(p.g.adj0 + (size_t)id * M0);
+                            radius = td[size - 1];
+                            if (limbo_n && radius < limbo_d)
+                                limbo_n = 0;
+                            if (ev_i != kNoNeighbor && !(ev_i & kExpandedBit) && ev_d == radius && limbo_n < kLimboCap) {
+                                if (lane == 0)
+                                    limbo()[limbo_n] = ev_i;
+                                limbo_n++, limbo_d = radius;
+                                __syncwarp();
+                            }
                         }
                     }
                 }
+                __syncwarp();
             }
-            __syncwarp();
+            if (level == 0 && size == 0) { // the descent is over: open the beam at `cur` (its distance is known; the
+                if (lane == 0) {           // reference measures it again, index.hpp:3436, so the counter advances)
+                    top_d()[0] = cur_d, top_i()[0] = cur;
+                    atomicOr(&vis[cur >> 5], 1u << (cur & 31));
+                    touched[0] = cur >> 5;
+                }
+                size = 1, cursor = 0, ntouched = 1;
+                st_dist += 1;
+                __syncwarp();
+            }
         }
         // un-visit only the words this walk touched
         if (ntouched <= p.touched_cap) {
@@ -466,34 +489,14 @@ template <int DM, int SK, int NQ> struct GroupWarp {
             for (size_t i = lane; i < p.words_per_slot; i += 32)
                 vis[i] = 0u;
         }
-        __syncwarp();
-        return size;
-    }
-
-    __device__ __forceinline__ void run_owner(uint32_t q) {
-        uint32_t* vis = p.vis + (size_t)(slot / p.G) * p.words_per_slot;
-        uint32_t* touched = p.touched + (size_t)(slot / p.G) * p.touched_cap;
-        uint32_t cur = p.g.entry;
-        if (lane == 0)
-            cand_id[0] = cur;
-        __syncwarp();
-        eval_round(1);
-        float cur_d = cand_d[0];
-        st_dist += 1;
-        __syncwarp();
-        uint32_t size = 0;
-        if (!dead)
-            greedy(cur, cur_d);
-        if (!dead)
-            size = beam(cur, cur_d, p.L, vis, touched);
         // results -> every rank (the all-gather of SURVEY 8e, fused); top is ascending, shrink(k), keys
         const uint32_t found = dead ? 0u : min(size, p.k);
         for (uint32_t i = lane; i < p.k; i += 32) {
             unsigned long long key = ~0ull;
             float d = INFINITY;
             if (i < found) {
-                key = __ldg(p.g.keys + (top_i[i] & kIdMask));
-                d = top_d[i];
+                key = __ldg(p.g.keys + (top_i()[i] & kIdMask));
+                d = top_d()[i];
             }
             for (uint32_t r = 0; r < p.G; ++r) {
                 p.res_keys[r][(size_t)q * p.k + i] = key;
@@ -502,65 +505,43 @@ template <int DM, int SK, int NQ> struct GroupWarp {
         }
         if ((uint32_t)lane < p.G)
             p.res_counts[lane][q] = found;
-        // release the helpers of this query
-        const uint32_t flag = p.flag_base + (++seq);
-        if ((uint32_t)lane < p.G && (uint32_t)lane != p.me)
-            st_sys_u64(p.req[lane] + (size_t)slot * (1 + cap), pack_word(kMsgDone, flag));
         __syncwarp();
     }
 };
 
 template <int DM, int SK, int NQ>
-__global__ void __launch_bounds__(kGroupThreads, 1) group_search_kernel(const __grid_constant__ GroupLaunch p) {
+__global__ void __launch_bounds__(kGroupThreads, 7) group_search_kernel(const __grid_constant__ GroupLaunch p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     GroupWarp<DM, SK, NQ> w(p);
     w.lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     w.slot = blockIdx.x * kGroupWarps + warp;
-    w.cap = p.cap;
     w.nchunks = p.g.row_bytes / 16;
-    const GroupWarpLayout lay = group_warp_layout(p.g.row_bytes, p.L, p.cap);
-    uint8_t* ws = smem_raw + (size_t)warp * lay.total;
-    w.qs = reinterpret_cast<uint4*>(ws + lay.q);
-    w.top_d = reinterpret_cast<float*>(ws + lay.top_d);
-    w.top_i = reinterpret_cast<uint32_t*>(ws + lay.top_i);
-    w.cand_id = reinterpret_cast<uint32_t*>(ws + lay.cand_id);
-    w.cand_d = reinterpret_cast<float*>(ws + lay.cand_d);
-    w.cand_slot = reinterpret_cast<uint16_t*>(ws + lay.cand_slot);
-    w.loc = ws + lay.loc;
-    w.limbo = reinterpret_cast<uint32_t*>(ws + lay.limbo);
+    w.ws = smem_raw + (size_t)warp * group_warp_layout(p.g.row_bytes, p.L, p.cap).total;
     w.seq = 0, w.last = p.flag_base, w.dead = false, w.a2 = 0.f;
+    w.waited = (p.me == p.root);
     w.st_dist = w.st_pops = w.st_hops = w.st_rounds = w.st_rows = 0;
-    w.rows = p.g.vectors, w.lo = p.bounds[p.me];
     w.t0 = globaltimer_ns();
 
     // the root's query staging buffer is complete when its kernel starts (stream order): tell everybody
     if (p.me == p.root && w.slot == 0 && (uint32_t)w.lane < p.G)
         st_sys_u64(p.qready[w.lane], (unsigned long long)p.epoch);
-    const uint32_t owner = w.slot % p.G; // W is a multiple of G: a slot keeps its owner for the whole launch
-    bool waited = (p.me == p.root);
-    for (uint32_t q = w.slot; q < p.nq; q += p.W) {
-        if (!waited) {
-            if (w.lane == 0) {
-                uint32_t spins = 0;
-                while (ld_sys_u64(p.qready[p.me]) != (unsigned long long)p.epoch) {
-                    if ((++spins & 2047u) == 0u && w.timed_out()) {
-                        w.dead = true;
-                        break;
-                    }
-                    __nanosleep(64);
-                }
-            }
-            w.dead = __any_sync(0xffffffffu, w.dead);
-            waited = true;
+    const uint32_t owner = w.slot % p.G;
+    if (owner == p.me) {
+        // this GPU's queries (q mod G == me) are handed to its owner warps as they become free
+        for (;;) {
+            uint32_t idx = 0;
+            if (w.lane == 0)
+                idx = (uint32_t)atomicAdd(&p.counters[6], 1ull);
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            const unsigned long long q = (unsigned long long)idx * p.G + p.me;
+            if (q >= p.nq || w.dead)
+                break;
+            w.run_owner((uint32_t)q);
         }
-        if (w.dead)
-            break;
-        w.load_query(q);
-        if (owner == p.me)
-            w.run_owner(q);
-        else
-            w.run_helper(owner);
+        w.tell_helpers(kMsgExit);
+    } else {
+        w.run_helper(owner);
     }
     // completion: results of this GPU's owners are visible system-wide before its done flag is
     __threadfence_system();
@@ -850,9 +831,7 @@ class GroupRank {
                 throw CudaError("group: the root rank must pass the queries");
             launch_cast_rows(d_queries, stride, kind, qbuf(), row_bytes, cfg.scalar_kind, cfg.dims, nq, stream);
         }
-        ++epoch;
-        if ((epoch & 0xFFFu) == 0u)
-            throw CudaError("group: flag space exhausted (re-create the group after 4095 searches)"); // see search_collective
+        ++epoch; // callers run renew_flags() first: (epoch & 0xFFF) is never 0 here
         GroupLaunch p;
         memset(&p, 0, sizeof(p));
         p.G = (uint32_t)world, p.me = (uint32_t)rank, p.W = W, p.cap = cap;
@@ -943,20 +922,34 @@ static uint32_t agree_W(Group& G, uint32_t L) {
     auto it = r0->W_for_L.find(L);
     if (it != r0->W_for_L.end())
         return it->second;
-    std::vector<std::vector<uint8_t>> mine(G.ranks.size(), std::vector<uint8_t>(4));
+    // every rank reports how many warps its device keeps resident for this beam width, and which physical device it is:
+    // ranks that share a device (a 1-GPU box running the G-rank protocol) must be resident together and split its warps
+    struct Offer {
+        uint32_t w;
+        char uuid[16];
+    };
+    std::vector<std::vector<uint8_t>> mine(G.ranks.size(), std::vector<uint8_t>(sizeof(Offer)));
     for (size_t i = 0; i < G.ranks.size(); ++i) {
-        uint32_t w = (uint32_t)G.ranks[i]->occupancy_for(L);
-        memcpy(mine[i].data(), &w, 4);
+        Offer o;
+        o.w = (uint32_t)G.ranks[i]->occupancy_for(L);
+        cudaDeviceProp prop;
+        LB_CUDA(cudaGetDeviceProperties(&prop, G.ranks[i]->device));
+        memcpy(o.uuid, prop.uuid.bytes, 16);
+        memcpy(mine[i].data(), &o, sizeof(o));
     }
     std::vector<uint8_t> all;
-    G.exchange(mine, all, 4);
-    uint32_t W = 0xFFFFFFFFu;
+    G.exchange(mine, all, sizeof(Offer));
+    const Offer* offers = (const Offer*)all.data();
+    uint32_t W = 0xFFFFFFFFu, share = 1;
     for (int r = 0; r < G.world; ++r) {
-        uint32_t w;
-        memcpy(&w, all.data() + 4 * r, 4);
-        W = std::min(W, w);
+        W = std::min(W, offers[r].w);
+        uint32_t same = 0;
+        for (int t = 0; t < G.world; ++t)
+            same += memcmp(offers[r].uuid, offers[t].uuid, 16) == 0;
+        share = std::max(share, same);
     }
     W = std::min(W, r0->Wmax);
+    W /= share;
     W -= W % (uint32_t)(G.world * kGroupWarps); // whole CTAs, and a slot keeps its owner across waves
     if (W == 0)
         throw CudaError("group: the search kernel does not fit on an SM (ef too large for shared memory)");
@@ -1000,6 +993,30 @@ void group_distribute(Group& G, Index* root_index, int root, size_t max_batch, s
     G.distributed = true;
 }
 
+// Message flags are (epoch mod 4096) << 20 | sequence number.  Before the 12-bit part wraps, every rank waits for its last
+// launch (which ends only when all ranks have finished theirs), all ranks meet, clear their mailboxes and meet again:
+// a word written 4096 launches ago can then never be mistaken for a fresh one.  Collective; costs two exchanges per 4095
+// searches.
+static void renew_flags(Group& G, const std::vector<cudaStream_t>& streams) {
+    GroupRank* r0 = G.ranks[0];
+    if (((r0->epoch + 1) & 0xFFFu) != 0u)
+        return;
+    std::vector<std::vector<uint8_t>> tick(G.ranks.size(), std::vector<uint8_t>(4, 0));
+    std::vector<uint8_t> all;
+    for (size_t i = 0; i < G.ranks.size(); ++i) {
+        LB_CUDA(cudaSetDevice(G.ranks[i]->device));
+        LB_CUDA(cudaStreamSynchronize(streams[i]));
+    }
+    G.exchange(tick, all, 4);
+    for (GroupRank* r : G.ranks) {
+        LB_CUDA(cudaSetDevice(r->device));
+        LB_CUDA(cudaMemset(r->slab + r->lay.req, 0, r->lay.res_keys - r->lay.req)); // request + response mailboxes
+        LB_CUDA(cudaDeviceSynchronize());
+        r->epoch += 1; // skip the value whose 12-bit part is 0 (flag 0 means "never written")
+    }
+    G.exchange(tick, all, 4);
+}
+
 static uint32_t beam_width(const GroupRank& r, size_t k, size_t ef) {
     size_t L = ef ? ef : r.cfg.ef;
     if (L < k)
@@ -1021,6 +1038,7 @@ void group_search_device(Group& G, const void* d_queries, size_t nq, size_t stri
     GroupRank* r = G.ranks[0];
     const uint32_t L = beam_width(*r, k, ef);
     const uint32_t W = agree_W(G, L);
+    renew_flags(G, std::vector<cudaStream_t>(1, stream));
     r->launch(d_queries, nq, stride, kind, k, L, W, G.root, d_keys, d_dists, d_counts, stream);
 }
 
@@ -1044,6 +1062,7 @@ void group_search_host(Group& G, const void* queries, size_t nq, size_t stride, 
             LB_CUDA(cudaStreamCreateWithFlags(&G.streams[i], cudaStreamNonBlocking));
         }
     }
+    renew_flags(G, G.streams);
     void* d_in = nullptr;
     for (size_t i = 0; i < nr; ++i) {
         GroupRank* r = G.ranks[i];
@@ -1145,7 +1164,7 @@ Group* group_create_local(const int* devices, int ndev) {
         for (int i = 0; i < ndev; ++i) {
             LB_CUDA(cudaSetDevice(G->ranks[i]->device));
             for (int j = 0; j < ndev; ++j) {
-                if (i == j)
+                if (i == j || G->ranks[i]->device == G->ranks[j]->device)
                     continue;
                 int can = 0;
                 LB_CUDA(cudaDeviceCanAccessPeer(&can, G->ranks[i]->device, G->ranks[j]->device));

@@ -3,9 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/lantern_b200.h"
 #include "engine.h"
-
-typedef void (*lb200_allgather_fn)(void* ctx, void const* send, void* recv, size_t bytes_per_rank);
 
 namespace lb200 {
 

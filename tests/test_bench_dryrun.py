@@ -81,7 +81,7 @@ def test_two_rank_glue_over_gloo(ref, big):
     env = dict(os.environ, DRYRUN_BIG="1" if big else "", MASTER_ADDR="127.0.0.1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(29731 + int(big)), os.path.join(ROOT, "tests", "dryrun_rank.py"), "--gpus", "2", "--workload", "tiny",
-           "--steps", "3", "--warmup", "3"]
+           "--steps", "3", "--warmup", "3", "--shard-mode", "graphs"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-3000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
