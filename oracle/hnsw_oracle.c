@@ -1146,8 +1146,10 @@ void ora_exact_search(const void* dataset, size_t n, size_t dataset_stride, cons
  * PQ codebook training.  Restates lantern_hnsw/src/hnsw/product_quantization.c:51-293 (k distinct dataset rows as
  * initial centres; assign by usearch_distance with strict '<'; centre = float mean of its members, empty clusters keep
  * their centre; stop when mean_c distance(old_c, new_c) <= 0.1 or after max_iter rounds; one k-means per subvector).
- * PARITY UNPINNED against a reference binary: that file needs postgres.h and cannot be compiled here, and its initial
- * rows come from Postgres' PRNG -- so the initial rows are an INPUT here (init_rows[nsub][ncent]).
+ * PARITY PINNED: the reference file itself is compiled unmodified into oracle/_ref/liboracle_refpq.so (oracle/Makefile
+ * target refpq, stand-in postgres.h in oracle/pg_shim/, PRNG scripted) and this function reproduces its codebooks bit for
+ * bit (tests/test_oracle_ref.py::test_kmeans_restatement_equals_the_reference).  The initial rows are an INPUT here
+ * (init_rows[nsub][ncent]): in the reference they come from libc/Postgres' PRNG.
  * ---------------------------------------------------------------------------------------- */
 int ora_kmeans(const float* data, size_t n, size_t dims, size_t nsub, size_t ncent, int metric, size_t max_iter,
                const uint32_t* init_rows, float* codebook) {

@@ -212,3 +212,31 @@ def exact_search(dataset, queries, k, metric="l2sq", quant="f32", dims=None, thr
                                keys.ctypes.data, keys.strides[0], dists.ctypes.data, dists.strides[0], C.byref(err))
     _check(err)
     return keys, dists
+
+
+# ---- the reference's k-means (product_quantization.c compiled unmodified: oracle/Makefile target refpq) ----------------
+SO_PQ = os.path.join(HERE, "_ref", "liboracle_refpq.so")
+_pqlib = None
+
+
+def pq_available():
+    return os.path.exists(SO_PQ) and available()
+
+
+def ref_kmeans(data, num_subvectors, num_centroids, init_rows, metric="l2sq", max_iter=20):
+    """product_quantization() of the reference from the given initial rows (init_rows[nsub][ncent], distinct per
+    subvector); returns the codebook tape float[num_centroids][dim]."""
+    global _pqlib
+    if _pqlib is None:
+        L = C.CDLL(SO_PQ)
+        L.refpq_train.restype = C.c_int
+        L.refpq_train.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]
+        _pqlib = L
+    data = np.ascontiguousarray(data, dtype=np.float32)
+    init_rows = np.ascontiguousarray(init_rows, dtype=np.uint32)
+    assert init_rows.shape == (num_subvectors, num_centroids)
+    assert all(len(set(r.tolist())) == num_centroids for r in init_rows), "initial rows must be distinct per subvector"
+    cb = np.zeros((num_centroids, data.shape[1]), np.float32)
+    _pqlib.refpq_train(data.ctypes.data, len(data), data.shape[1], num_subvectors, num_centroids, METRIC[metric], max_iter,
+                       init_rows.ctypes.data, cb.ctypes.data)
+    return cb

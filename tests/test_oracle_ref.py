@@ -236,3 +236,29 @@ def test_batched_build_model_is_deterministic_and_as_good_as_sequential(port):
         for level in range(b.level(slot) + 1):
             for nb in b.neighbors(slot, level):
                 assert b.level(int(nb)) >= level
+
+
+@pytest.mark.parametrize("metric,scale", [("l2sq", 3.0), ("l2sq", 8.0), ("cos", 3.0)])
+def test_kmeans_restatement_equals_the_reference(ref, port, metric, scale):
+    """PQ codebook training: the UNMODIFIED reference k-means (lantern_hnsw/src/hnsw/product_quantization.c compiled against
+    the stand-in postgres.h of oracle/pg_shim/, PRNG scripted so that both sides start from the same rows) against the
+    plain-C restatement ora_kmeans -- bit for bit, for 1, 3 and up to 25 Lloyd rounds, which pins row (f4) of SURVEY 8."""
+    if not ref.pq_available():
+        pytest.skip("oracle/_ref/liboracle_refpq.so not built")
+    rng = np.random.default_rng(6)
+    n, d, nsub, ncent = 3000, 24, 4, 16
+    centers = rng.standard_normal((ncent, d)).astype(np.float32) * scale
+    X = (centers[rng.integers(0, ncent, n)] + rng.standard_normal((n, d))).astype(np.float32)
+    init = np.stack([rng.choice(n, ncent, replace=False) for _ in range(nsub)]).astype(np.uint32)
+    seen_rounds = set()
+    for it in (1, 3, 25):
+        rcb = ref.ref_kmeans(X, nsub, ncent, init, metric, it)
+        pcb, rounds = port.kmeans(X, nsub, ncent, init, metric, it)
+        assert np.array_equal(rcb.view(np.uint32), pcb.view(np.uint32)), np.abs(rcb - pcb).max()
+        seen_rounds.add(rounds)
+    if metric == "l2sq":
+        assert max(seen_rounds) > 3  # the stop rule (mean centre shift <= 0.1) was exercised beyond the early rounds
+    # the hnsw_pq_index.sql fixture geometry: k == n, every init is a permutation, one round moves nothing
+    Xc = np.repeat((np.arange(10) * 0.1).astype(np.float32)[:, None], 16, axis=1)
+    perm = np.stack([rng.permutation(10) for _ in range(4)]).astype(np.uint32)
+    assert np.array_equal(ref.ref_kmeans(Xc, 4, 10, perm, "l2sq", 20), port.kmeans(Xc, 4, 10, perm, "l2sq", 20)[0])
