@@ -287,9 +287,9 @@ static void build_pending_impl(Index& idx) {
         throw CudaError("build: vectors wider than 8192 bytes are not supported");
     const uint32_t top_cap = (uint32_t)std::max<size_t>(cfg.efc, M0 + 2);
     const GraphView gv0 = idx.view();
-    const size_t smem_ins = cfg.pq ? walk_layout_pq(gv0.num_subvectors, gv0.pq_lut_width, gv0.dims, top_cap, M0 + 1).total
+    const size_t smem_ins = cfg.pq ? walk_layout_pq(gv0.num_subvectors, gv0.pq_lut_width, pq_value_floats(gv0), top_cap, M0 + 1).total
                                    : walk_layout(R, row_bytes, top_cap, M0 + 1).total;
-    const size_t smem_rev = (cfg.pq ? walk_layout_pq(gv0.num_subvectors, gv0.pq_lut_width, gv0.dims, M0 + 2, M0 + 1).total
+    const size_t smem_rev = (cfg.pq ? walk_layout_pq(gv0.num_subvectors, gv0.pq_lut_width, pq_value_floats(gv0), M0 + 2, M0 + 1).total
                                     : walk_layout(R, row_bytes, M0 + 2, M0 + 1).total) + (size_t)M0 * 8;
     int occ_ins = 0, occ_rev = 0;
     dispatch_walker(cfg.pq, idx.dist_mode_, cfg.scalar_kind, nq, [&](auto tag) {

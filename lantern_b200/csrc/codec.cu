@@ -140,7 +140,77 @@ __global__ void pq_tables_kernel(const float* __restrict__ codebook, uint32_t di
     }
 }
 
+// Per-query ADC tables for a whole batch (the value side of lantern_storage.hpp:249-270 / index_dense.hpp:341-358 is the raw
+// query): table[q][s * W + c] = |q_s - c_{c,s}|^2 (l2sq) or q_s . c_{c,s} (cos), dimensions accumulated in ascending order with
+// fmaf -- the same arithmetic PqEval::entry performs when a kernel builds the table itself -- and |q|^2 behind the table.
+// One CTA per query; the 0.75 MB of centroid slices it touches stay in L2 across the batch.
+__global__ void pq_query_tables_kernel(const float* __restrict__ codebook, uint32_t dims, uint32_t nsub, uint32_t W, int cosine,
+                                       const float* __restrict__ queries, size_t q_stride, float* __restrict__ tables,
+                                       size_t table_floats) {
+    extern __shared__ float qs[];
+    const uint32_t q = blockIdx.x, sd = dims / nsub;
+    const float* src = queries + (size_t)q * q_stride;
+    for (uint32_t i = threadIdx.x; i < dims; i += blockDim.x)
+        qs[i] = src[i];
+    __syncthreads();
+    float* out = tables + (size_t)q * table_floats;
+    for (uint32_t e = threadIdx.x; e < nsub * W; e += blockDim.x) {
+        const uint32_t s = e / W, c = e - s * W;
+        const float* cen = codebook + (size_t)c * dims + (size_t)s * sd;
+        const float* v = qs + (size_t)s * sd;
+        float acc = 0.f;
+        if ((sd & 3u) == 0u) {
+            for (uint32_t i = 0; i < sd; i += 4) {
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cen + i));
+                if (cosine) {
+                    acc = fmaf(v[i], c4.x, acc), acc = fmaf(v[i + 1], c4.y, acc);
+                    acc = fmaf(v[i + 2], c4.z, acc), acc = fmaf(v[i + 3], c4.w, acc);
+                } else {
+                    float d = v[i] - c4.x;
+                    acc = fmaf(d, d, acc);
+                    d = v[i + 1] - c4.y, acc = fmaf(d, d, acc);
+                    d = v[i + 2] - c4.z, acc = fmaf(d, d, acc);
+                    d = v[i + 3] - c4.w, acc = fmaf(d, d, acc);
+                }
+            }
+        } else {
+            for (uint32_t i = 0; i < sd; ++i) {
+                const float cv = __ldg(cen + i);
+                if (cosine)
+                    acc = fmaf(v[i], cv, acc);
+                else {
+                    const float d = v[i] - cv;
+                    acc = fmaf(d, d, acc);
+                }
+            }
+        }
+        out[e] = acc;
+    }
+    if (threadIdx.x < 32) { // |q|^2 with the lane layout of PqEval::load_value
+        float p2 = 0.f;
+        for (uint32_t i = threadIdx.x; i < dims; i += 32)
+            p2 += qs[i] * qs[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+        if (threadIdx.x < 4)
+            out[(size_t)nsub * W + threadIdx.x] = threadIdx.x == 0 ? p2 : 0.f;
+    }
+}
+
 } // namespace
+
+void launch_pq_query_tables(const float* d_codebook, size_t dims, size_t nsub, size_t lut_width, bool cosine, const float* d_queries,
+                            size_t q_stride_floats, size_t nq, float* d_tables, cudaStream_t stream) {
+    if (!nq)
+        return;
+    const size_t table_floats = nsub * lut_width + 4;
+    pq_query_tables_kernel<<<(unsigned)nq, 256, dims * sizeof(float), stream>>>(d_codebook, (uint32_t)dims, (uint32_t)nsub,
+                                                                                (uint32_t)lut_width, cosine ? 1 : 0, d_queries,
+                                                                                q_stride_floats, d_tables, table_floats);
+    LB_CUDA(cudaGetLastError());
+    count_launch();
+}
 
 void launch_pq_tables(const float* d_codebook, size_t dims, size_t ncent, size_t nsub, bool cosine, float* d_pair, float* d_norm,
                       cudaStream_t stream) {

@@ -70,7 +70,7 @@ Index::Index(const IndexConfig& cfg, const float* codebook) : cfg_(cfg) {
         LB_CUDA(cudaMalloc(&d_pq_pair_, cfg.num_subvectors * cfg.num_centroids * cfg.num_centroids * sizeof(float)));
         LB_CUDA(cudaMalloc(&d_pq_norm_, cfg.num_subvectors * cfg.num_centroids * sizeof(float)));
         launch_pq_tables(d_codebook_, cfg.dims, cfg.num_centroids, cfg.num_subvectors, dist_mode_ == DM_COS, d_pq_pair_, d_pq_norm_, 0);
-        if ((cfg.num_subvectors * std::min<size_t>(cfg.num_centroids, 128) + cfg.dims) * 4 > 200 * 1024)
+        if ((cfg.num_subvectors * std::min<size_t>(cfg.num_centroids, 128) + cfg.dims + 520) * 4 > 200 * 1024)
             throw CudaError("pq: num_subvectors * num_centroids look-up table does not fit in shared memory");
     } else {
         stored_bytes_ = vec_bytes_;
@@ -86,7 +86,7 @@ Index::~Index() {
     cudaFree(d_vectors_), cudaFree(d_adj0_), cudaFree(d_upper_ref_), cudaFree(d_upper_adj_), cudaFree(d_keys_);
     cudaFree(d_codebook_), cudaFree(scratch_.visited), cudaFree(scratch_.touched), cudaFree(scratch_.counters);
     cudaFree(d_query_buf_), cudaFree(d_io_buf_);
-    cudaFree(d_pq_pair_), cudaFree(d_pq_norm_), cudaFree(d_pending_raw_);
+    cudaFree(d_pq_pair_), cudaFree(d_pq_norm_), cudaFree(d_pending_raw_), cudaFree(d_pq_tables_);
     if (ev0_)
         cudaEventDestroy(ev0_);
     if (ev1_)
@@ -330,12 +330,30 @@ void Index::search_device(const void* d_queries, size_t nq, size_t stride, int k
     launch_cast_rows(d_queries, stride, kind, qbuf, qrow, cfg_.pq ? (int)SK_F32 : cfg_.scalar_kind, cfg_.dims, nq, stream);
 
     const uint32_t expand = (uint32_t)std::min<size_t>(std::max<size_t>(search_expand_, 1), 8);
-    const uint32_t max_ctas = search_max_ctas(dist_mode_, cfg_.scalar_kind, view(), (uint32_t)L, cfg_.pq, expand);
+    GraphView gv = view();
+    if (cfg_.pq) {
+        // the batch's look-up tables in one dense launch (49 KB per query at 96 x 128): the walk kernel then fetches a table with
+        // one bulk copy instead of computing nsub * ncent * subdim flops per query at 4 CTAs per SM
+        const size_t tbytes = nq * (cfg_.num_subvectors * (size_t)gv.pq_lut_width + 4) * sizeof(float);
+        if (tbytes <= ((size_t)1 << 30)) {
+            if (tbytes > pq_tables_bytes_) {
+                if (d_pq_tables_)
+                    LB_CUDA(cudaFree(d_pq_tables_));
+                d_pq_tables_ = nullptr;
+                pq_tables_bytes_ = round_up(tbytes + tbytes / 4, 256);
+                LB_CUDA(cudaMalloc(&d_pq_tables_, pq_tables_bytes_));
+            }
+            launch_pq_query_tables(d_codebook_, cfg_.dims, cfg_.num_subvectors, gv.pq_lut_width, dist_mode_ == DM_COS, (const float*)qbuf,
+                                   qrow / sizeof(float), nq, d_pq_tables_, stream);
+            gv.pq_query_tables = d_pq_tables_;
+        }
+    }
+    const uint32_t max_ctas = search_max_ctas(dist_mode_, cfg_.scalar_kind, gv, (uint32_t)L, cfg_.pq, expand);
     ensure_scratch(max_ctas);
     LB_CUDA(cudaMemsetAsync(scratch_.counters, 0, 4 * sizeof(unsigned long long), stream));
 
     SearchLaunch p{};
-    p.g = view();
+    p.g = gv;
     p.s = scratch_;
     p.s.ctas = max_ctas;
     p.queries = qbuf;

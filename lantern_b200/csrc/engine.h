@@ -54,6 +54,7 @@ struct GraphView {
     const float* codebook; // [num_centroids][dims]
     const float* pq_pair;  // [nsub][ncent][ncent] centroid-pair table (l2sq: |ca-cb|^2 ; cos: ca.cb)
     const float* pq_norm;  // [nsub][ncent] |centroid slice|^2 (cos)
+    const float* pq_query_tables; // search only: per-query look-up tables [nq][pq_table_floats] precomputed for the batch, or NULL
     uint32_t flags;        // tuning: 1 = L2-prefetch the adjacency of every measured node, 2 = of accepted nodes only
     uint32_t dims, num_centroids, num_subvectors;
     uint32_t pq_lut_width; // centroids the per-value table covers (= num_centroids, or 128 when every stored code is < 128)
@@ -135,6 +136,8 @@ class Index {
     float* d_codebook_ = nullptr;
     float* d_pq_pair_ = nullptr;
     float* d_pq_norm_ = nullptr;
+    float* d_pq_tables_ = nullptr; // per-query look-up tables of the current search batch
+    size_t pq_tables_bytes_ = 0;
     uint32_t pq_max_code_ = 0; // largest centroid id present in the stored codes
     float* d_pending_raw_ = nullptr; // pq: raw f32 rows of the pending vectors (the value side of build distances)
     size_t pending_raw_cap_ = 0;
@@ -179,6 +182,9 @@ void launch_pq_encode(const float* d_codebook, size_t dims, size_t ncent, size_t
                       cudaStream_t stream);
 void launch_pq_tables(const float* d_codebook, size_t dims, size_t ncent, size_t nsub, bool cosine, float* d_pair, float* d_norm,
                       cudaStream_t stream);
+// per-query ADC tables of a batch: out[q][s * lut_width + c] (+ |q|^2 at [nsub * lut_width]), row stride = nsub*lut_width + 4 floats
+void launch_pq_query_tables(const float* d_codebook, size_t dims, size_t nsub, size_t lut_width, bool cosine, const float* d_queries,
+                            size_t q_stride_floats, size_t nq, float* d_tables, cudaStream_t stream);
 void launch_pq_decode(const float* d_codebook, size_t dims, size_t ncent, size_t nsub, const uint8_t* d_codes,
                       size_t code_stride, size_t n, float* d_vecs, cudaStream_t stream);
 // search.cu

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(kWalkThreads) hnsw_search_kernel(const __grid_
         const uint32_t q = sm.ctrl->item;
         if (q >= p.nq)
             break;
-        w.load_value(p.queries + (size_t)q * p.query_stride);
+        w.load_query(q, p.queries + (size_t)q * p.query_stride);
 
         uint32_t cur = p.g.entry;
         float cur_d = w.measure_one(cur);
@@ -92,7 +92,7 @@ template <class W> int occupancy_one(size_t smem) {
 } // namespace
 
 static size_t search_smem(const GraphView& g, bool pq, uint32_t R, uint32_t L, uint32_t expand) {
-    return pq ? walk_layout_pq(g.num_subvectors, g.pq_lut_width, g.dims, L, g.M0 * expand).total
+    return pq ? walk_layout_pq(g.num_subvectors, g.pq_lut_width, pq_value_floats(g), L, g.M0 * expand).total
               : walk_layout(R, g.row_bytes, L, g.M0 * expand).total;
 }
 

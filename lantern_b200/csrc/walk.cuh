@@ -73,10 +73,15 @@ __host__ __device__ inline WalkLayout walk_layout_bytes(size_t stage_bytes, uint
 __host__ __device__ inline WalkLayout walk_layout(uint32_t R, uint32_t row_bytes, uint32_t top_cap, uint32_t cand_cap) {
     return walk_layout_bytes((size_t)R * row_bytes, R, top_cap, cand_cap);
 }
-// PQ: look-up table [nsub][ncent] + value staging [dims]
-__host__ __device__ inline WalkLayout walk_layout_pq(uint32_t nsub, uint32_t lut_width, uint32_t dims, uint32_t top_cap, uint32_t cand_cap) {
-    return walk_layout_bytes(((size_t)nsub * lut_width + dims) * 4, 0, top_cap, cand_cap);
+// PQ: look-up table [nsub][ncent] (+ 4 floats: the value's squared norm travels with a precomputed table) + value staging
+// [dims] + per-warp partial sums [warps][2][64]; one mbarrier (bulk copy of a precomputed table)
+constexpr uint32_t kPqPartPerWarp = 64;
+__host__ __device__ inline size_t pq_table_floats(uint32_t nsub, uint32_t lut_width) { return (size_t)nsub * lut_width + 4; }
+// `value_floats` = dims when the kernel builds tables itself from raw vectors (build; search without precomputed tables), else 0
+__host__ __device__ inline WalkLayout walk_layout_pq(uint32_t nsub, uint32_t lut_width, uint32_t value_floats, uint32_t top_cap, uint32_t cand_cap) {
+    return walk_layout_bytes((pq_table_floats(nsub, lut_width) + value_floats + (size_t)kWalkWarps * 2 * kPqPartPerWarp) * 4, 1, top_cap, cand_cap);
 }
+__host__ __device__ inline uint32_t pq_value_floats(const GraphView& g) { return g.pq_query_tables ? 0u : g.dims; }
 
 inline uint32_t pick_ring_slots(uint32_t row_bytes) {
     uint32_t budget = 24u * 1024u; // 8 slots of a d=768 f32 row: 8 CTAs/SM; measured best on B200 (profiles/)
@@ -255,6 +260,7 @@ template <int DM, int SK, int NQ> struct RowEval : WalkBase {
     }
     // a stored node becomes the value (refine_: candidate vs accepted; reverse links: target vs its neighbours)
     __device__ __forceinline__ void load_node(uint32_t id) { load_value(g.vectors + (size_t)id * g.row_bytes); }
+    __device__ __forceinline__ void load_query(uint32_t, const uint8_t* row) { load_value(row); }
 
     __device__ __forceinline__ void issue(uint32_t slot, uint32_t id) {
         uint64_t* bar = &sm.full[slot];
@@ -309,19 +315,58 @@ template <int DM, int SK, int NQ> struct RowEval : WalkBase {
 // [nsub][ncent][ncent] precomputed at index creation.  Code rows (nsub bytes) are read straight from HBM/L2.
 template <int DM> struct PqEval : WalkBase {
     static __host__ __device__ WalkLayout layout(const GraphView& g, uint32_t, uint32_t top_cap, uint32_t cand_cap) {
-        return walk_layout_pq(g.num_subvectors, g.pq_lut_width, g.dims, top_cap, cand_cap);
+        return walk_layout_pq(g.num_subvectors, g.pq_lut_width, pq_value_floats(g), top_cap, cand_cap);
     }
-    float* lut;  // shared [nsub][ncent]
+    float* lut;  // shared [nsub][ncent] (+ 4)
     float* qbuf; // shared [dims]
+    float* part; // shared [warps][2][64]: per-chunk partial sums of the candidates a warp is measuring
     float a2;
+    uint32_t tphase;
 
     __device__ __forceinline__ explicit PqEval(const GraphView& gv) : WalkBase(gv) {}
     __device__ __forceinline__ void init(uint8_t* smem_raw, const WalkLayout& lay, uint32_t, const SearchScratch& s) {
         init_base(smem_raw, lay, s);
         lut = reinterpret_cast<float*>(smem_raw);
-        qbuf = lut + (size_t)g.num_subvectors * g.pq_lut_width;
+        qbuf = lut + pq_table_floats(g.num_subvectors, g.pq_lut_width);
+        part = qbuf + pq_value_floats(g);
         a2 = 0.f;
+        tphase = 0;
+        if (threadIdx.x == 0) {
+            mbar_init(&sm.full[0], 1);
+            fence_mbar_init();
+        }
         __syncthreads();
+    }
+
+    // one table entry: |v_s - c|^2 (l2sq) or v_s . c (cos), dimensions in ascending order (the order pq_query_tables_kernel uses)
+    __device__ __forceinline__ static float entry(const float* qs, const float* cen, uint32_t sd) {
+        float acc = 0.f;
+        if ((sd & 3u) == 0u) {
+            for (uint32_t i = 0; i < sd; i += 4) {
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cen + i));
+                if constexpr (DM == DM_COS) {
+                    acc = fmaf(qs[i], c4.x, acc), acc = fmaf(qs[i + 1], c4.y, acc);
+                    acc = fmaf(qs[i + 2], c4.z, acc), acc = fmaf(qs[i + 3], c4.w, acc);
+                } else {
+                    float d = qs[i] - c4.x;
+                    acc = fmaf(d, d, acc);
+                    d = qs[i + 1] - c4.y, acc = fmaf(d, d, acc);
+                    d = qs[i + 2] - c4.z, acc = fmaf(d, d, acc);
+                    d = qs[i + 3] - c4.w, acc = fmaf(d, d, acc);
+                }
+            }
+        } else {
+            for (uint32_t i = 0; i < sd; ++i) {
+                const float cv = __ldg(cen + i);
+                if constexpr (DM == DM_COS)
+                    acc = fmaf(qs[i], cv, acc);
+                else {
+                    const float d = qs[i] - cv;
+                    acc = fmaf(d, d, acc);
+                }
+            }
+        }
+        return acc;
     }
 
     // `row` = raw f32 vector (dims floats) in global memory
@@ -333,28 +378,35 @@ template <int DM> struct PqEval : WalkBase {
             qbuf[i] = __ldg(q + i);
         __syncthreads();
         if constexpr (DM == DM_COS) {
-            float part = 0.f;
+            float p2 = 0.f;
             for (uint32_t i = lane; i < dims; i += 32)
-                part += qbuf[i] * qbuf[i];
-            a2 = warp_sum(part);
+                p2 += qbuf[i] * qbuf[i];
+            a2 = warp_sum(p2);
         }
         for (uint32_t e = threadIdx.x; e < nsub * ncent; e += kWalkThreads) {
             const uint32_t s = e / ncent, c = e - s * ncent;
-            const float* cen = g.codebook + (size_t)c * dims + (size_t)s * sd;
-            const float* qs = qbuf + (size_t)s * sd;
-            float acc = 0.f;
-            for (uint32_t i = 0; i < sd; ++i) {
-                const float cv = __ldg(cen + i);
-                if constexpr (DM == DM_COS)
-                    acc = fmaf(qs[i], cv, acc);
-                else {
-                    const float d = qs[i] - cv;
-                    acc = fmaf(d, d, acc);
-                }
-            }
-            lut[e] = acc;
+            lut[e] = entry(qbuf + (size_t)s * sd, g.codebook + (size_t)c * dims + (size_t)s * sd, sd);
         }
         __syncthreads();
+    }
+
+    // search: query `qi` of the batch.  When the batch's tables were precomputed (pq_query_tables_kernel, one dense launch at
+    // full occupancy instead of nsub*ncent*subdim flops per query inside this 4-CTA/SM kernel) the table is one bulk copy away.
+    __device__ __forceinline__ void load_query(uint32_t qi, const uint8_t* row) {
+        if (!g.pq_query_tables) {
+            load_value(row);
+            return;
+        }
+        const uint32_t floats = (uint32_t)pq_table_floats(g.num_subvectors, g.pq_lut_width);
+        __syncthreads(); // every look-up of the previous query is done
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&sm.full[0], floats * 4);
+            bulk_g2s(lut, g.pq_query_tables + (size_t)qi * floats, floats * 4, &sm.full[0]);
+        }
+        mbar_wait(&sm.full[0], tphase);
+        tphase ^= 1u;
+        a2 = lut[(size_t)g.num_subvectors * g.pq_lut_width]; // |query|^2 (cos)
     }
 
     __device__ __forceinline__ void load_node(uint32_t id) {
@@ -366,40 +418,101 @@ template <int DM> struct PqEval : WalkBase {
             lut[e] = __ldg(g.pq_pair + ((size_t)s * full + __ldg(codes + s)) * full + c);
         }
         if constexpr (DM == DM_COS) {
-            float part = 0.f;
+            float p2 = 0.f;
             for (uint32_t s = lane; s < nsub; s += 32)
-                part += __ldg(g.pq_norm + (size_t)s * full + __ldg(codes + s));
-            a2 = warp_sum(part);
+                p2 += __ldg(g.pq_norm + (size_t)s * full + __ldg(codes + s));
+            a2 = warp_sum(p2);
         }
         __syncthreads();
     }
 
-    __device__ __forceinline__ void eval(uint32_t n) {
-        const uint32_t ncent = g.pq_lut_width, full = g.num_centroids, nsub = g.num_subvectors, words = (nsub + 3) / 4;
-        for (uint32_t j = warp; j < n; j += kWalkWarps) {
-            const uint32_t* row = reinterpret_cast<const uint32_t*>(g.vectors + (size_t)sm.cand_id[j] * g.row_bytes);
-            float acc = 0.f, b2 = 0.f;
-            for (uint32_t wi = lane; wi < words; wi += 32) {
-                const uint32_t w32 = __ldg(row + wi);
+    // 16 codes of one chunk -> partial sums
+    __device__ __forceinline__ void chunk_sums(const uint4& v, uint32_t ch, float& acc, float& b2) const {
+        const uint32_t ncent = g.pq_lut_width, full = g.num_centroids, nsub = g.num_subvectors;
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        acc = 0.f, b2 = 0.f;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const uint32_t s = 4 * wi + b;
-                    if (s < nsub) {
-                        const uint32_t c = (w32 >> (8 * b)) & 255u;
-                        acc += lut[s * ncent + c];
-                        if constexpr (DM == DM_COS)
-                            b2 += __ldg(g.pq_norm + (size_t)s * full + c);
-                    }
+        for (int wi = 0; wi < 4; ++wi)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t s = ch * 16 + wi * 4 + b;
+                if (s < nsub) {
+                    const uint32_t c = (w[wi] >> (8 * b)) & 255u;
+                    acc += lut[s * ncent + c];
+                    if constexpr (DM == DM_COS)
+                        b2 += __ldg(g.pq_norm + (size_t)s * full + c);
                 }
             }
-            acc = warp_sum(acc);
-            float d = acc;
-            if constexpr (DM == DM_COS) {
-                b2 = warp_sum(b2);
-                d = cos_from_parts(acc, a2, b2);
+    }
+
+    // distances value -> cand_id[0..n).  Candidate j belongs to warp j % 4.  A warp fetches the code rows of ALL its candidates of
+    // a pass at once (16-byte chunks, two per lane, every load issued before the first look-up -- one HBM latency per round
+    // instead of one per candidate), each lane sums the 16 look-ups of its chunks, and the chunk sums of a candidate are added
+    // in ascending chunk order (a fixed order: the distance does not depend on which lane or pass served the candidate).
+    __device__ __forceinline__ void eval(uint32_t n) {
+        const uint32_t cpr = g.row_bytes / 16; // chunks per code row (6 at 96 subvectors)
+        const uint32_t T = n > (uint32_t)warp ? (n - warp + kWalkWarps - 1) / kWalkWarps : 0;
+        float* pa = part + (size_t)warp * 2 * kPqPartPerWarp;
+        float* pb = pa + kPqPartPerWarp;
+        if (cpr <= kPqPartPerWarp) {
+            const uint32_t per_pass = kPqPartPerWarp / cpr; // whole candidates per pass
+            for (uint32_t t0 = 0; t0 < T; t0 += per_pass) {
+                const uint32_t cnt = min(per_pass, T - t0), chunks = cnt * cpr;
+                uint4 v[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const uint32_t idx = lane + 32 * u;
+                    if (idx < chunks) {
+                        const uint32_t t = idx / cpr, ch = idx - t * cpr;
+                        const uint32_t id = sm.cand_id[warp + kWalkWarps * (t0 + t)];
+                        v[u] = __ldg(reinterpret_cast<const uint4*>(g.vectors + (size_t)id * g.row_bytes) + ch);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const uint32_t idx = lane + 32 * u;
+                    if (idx < chunks) {
+                        const uint32_t t = idx / cpr, ch = idx - t * cpr;
+                        float acc, b2;
+                        chunk_sums(v[u], ch, acc, b2);
+                        pa[idx] = acc;
+                        if constexpr (DM == DM_COS)
+                            pb[idx] = b2;
+                    }
+                }
+                __syncwarp();
+                if ((uint32_t)lane < cnt) {
+                    float acc = 0.f, b2 = 0.f;
+                    for (uint32_t ch = 0; ch < cpr; ++ch) {
+                        acc += pa[lane * cpr + ch];
+                        if constexpr (DM == DM_COS)
+                            b2 += pb[lane * cpr + ch];
+                    }
+                    float d = acc;
+                    if constexpr (DM == DM_COS)
+                        d = cos_from_parts(acc, a2, b2);
+                    sm.cand_d[warp + kWalkWarps * (t0 + lane)] = d;
+                }
+                __syncwarp();
             }
-            if (lane == 0)
-                sm.cand_d[j] = d;
+        } else { // very wide code rows (> 1024 subvectors): one candidate at a time, chunks strided over the lanes
+            for (uint32_t t = 0; t < T; ++t) {
+                const uint32_t id = sm.cand_id[warp + kWalkWarps * t];
+                float acc = 0.f, b2 = 0.f;
+                for (uint32_t ch = lane; ch < cpr; ch += 32) {
+                    float a1, b1;
+                    chunk_sums(__ldg(reinterpret_cast<const uint4*>(g.vectors + (size_t)id * g.row_bytes) + ch), ch, a1, b1);
+                    acc += a1, b2 += b1;
+                }
+                acc = warp_sum(acc);
+                float d = acc;
+                if constexpr (DM == DM_COS) {
+                    b2 = warp_sum(b2);
+                    d = cos_from_parts(acc, a2, b2);
+                }
+                if (lane == 0)
+                    sm.cand_d[warp + kWalkWarps * t] = d;
+            }
         }
     }
 };

@@ -133,6 +133,19 @@ for M in (16, 4):
         off += 10 + 4 + 12 * M + l * (4 + 6 * M) + 8
     out["levels_M%d" % M] = np.array(lv, np.int16)
 
+# --- usearch_exact_search (lib.cpp:450-481) on tie-free continuous data: OFFSETS and distances are pinned (k = 1 takes the
+#     min_element branch of exact_search_t, index_plugins.hpp:1636-1650; k = 10 the partial_sort branch) ---
+rng2 = np.random.default_rng(77)
+for metric in ("l2sq", "cos"):
+    X = rng2.standard_normal((500, 24)).astype(np.float32)
+    Q = rng2.standard_normal((32, 24)).astype(np.float32)
+    out["exact_%s_X" % metric], out["exact_%s_Q" % metric] = X, Q
+    for kk in (1, 10):
+        ek, ed = reflib.exact_search(X, Q, kk, metric)
+        out["exact_%s_k%d_offsets" % (metric, kk)], out["exact_%s_k%d_dists" % (metric, kk)] = ek, ed
+        gaps = np.diff(np.sort(np.array([reflib.distance(q, x, metric) for q in Q[:4] for x in X]).reshape(4, -1), axis=1)[:, :12], axis=1)
+        assert gaps.min() > 1e-6  # tie-free: the offsets are well defined
+
 path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_v1.npz")
 np.savez_compressed(path, **out)
 print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")

@@ -68,6 +68,16 @@ def test_reference_file_loads_and_sequential_build_reproduces_it(eng, name, metr
     assert np.allclose(ed, G[name + "_exact_dists"], rtol=1e-6, atol=1e-6)
 
 
+@pytest.mark.parametrize("metric", ["l2sq", "cos"])
+def test_exact_search_offsets_golden(eng, metric):
+    """lb200_exact_search against the offsets usearch_exact_search itself returned (tests/golden, tie-free data)."""
+    X, Q = G["exact_%s_X" % metric], G["exact_%s_Q" % metric]
+    for kk in (1, 10):
+        ek, ed = eng.exact_search(X, Q, kk, metric)
+        assert np.array_equal(ek, G["exact_%s_k%d_offsets" % (metric, kk)])
+        assert np.allclose(ed, G["exact_%s_k%d_dists" % (metric, kk)], rtol=1e-5, atol=1e-6)
+
+
 def test_distance_kernels(eng, port):
     A, B = G["dist_A"], G["dist_B"]
     for metric in ("l2sq", "cos"):
