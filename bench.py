@@ -694,17 +694,46 @@ def run_ours(args, wl):
             ridx.add_batch(np.arange(1, n_ref + 1, dtype=np.uint64), Xr, threads=cores)
             t_rb = time.perf_counter() - t0
             qh = Q.cpu().numpy()
-            spent, done, s = 0.0, 0, 0
+            spent, done, s, first = 0.0, 0, 0, None
             while spent < args.cpu_seconds and s < pool:
                 t0 = time.perf_counter()
-                ridx.search_batch(qh[s * B:(s + 1) * B], k, threads=cores)
+                rres = ridx.search_batch(qh[s * B:(s + 1) * B], k, threads=cores)
                 spent += time.perf_counter() - t0
+                if first is None:
+                    first = rres
                 done += B
                 s += 1
             cpu_baseline = {"value": done / spent, "unit": "queries/s", "cores": cores, "kind": "reference",
                             "sample": "unmodified usearch (oracle/_ref) builds its own pq graph over the first %d of %d rows (%.0f s) "
                                       "with the same codebook and searches %d queries (%.1f s) on %d threads" % (
                                           n_ref, n, t_rb, done, spent, cores)}
+            # parity at this geometry.  The reference cannot LOAD a pq index file (lantern_storage.hpp:550-551), so a same-graph
+            # comparison is impossible: the engine builds its own pq graph over the SAME rows with the same codebook, both answer
+            # the same queries, both are scored against the raw-fp32 exact top-k of those rows (the +-0.5 % recall contract)
+            Xd = torch.from_numpy(Xr).to(dev)
+            eidx = api.Index(dim, wl["metric"], "f32", M=wl["M"], efc=wl["efc"], ef=ef, pq=True, num_centroids=pq[1],
+                             num_subvectors=pq[0], codebook=codebook)
+            eidx.reserve(n_ref)
+            eidx.add_batch_device(np.arange(1, n_ref + 1, dtype=np.uint64), Xd.data_ptr(), n_ref, rowb, "f32")
+            eidx.build()
+            ptk = torch.empty((nrec, k), dtype=torch.int64, device=dev)
+            ptd = torch.empty((nrec, k), dtype=torch.float32, device=dev)
+            api.exact_search_device(Xd.data_ptr(), n_ref, rowb, Q.data_ptr(), nrec, rowb, k, ptk.data_ptr(), ptd.data_ptr(), wl["metric"],
+                                    "f32", dim, stream.cuda_stream)
+            eidx.search_batch_device(Q.data_ptr(), B, rowb, "f32", k, ef, out_keys.data_ptr(), out_dists.data_ptr(),
+                                     out_counts.data_ptr(), stream.cuda_stream)
+            torch.cuda.synchronize()
+            ptruth = (ptk + 1).cpu().numpy()
+            ek = out_keys[:nrec].cpu().numpy().astype(np.uint64)
+            rk = first[0][:nrec]
+            parity = {"graph_rows": n_ref, "queries": nrec, "same_graph": False,
+                      "why": "the reference refuses to load pq index files; each side builds its own graph over the same rows with the "
+                             "same codebook",
+                      "reference_recall_at_k": recall_at_k(rk, ptruth), "engine_recall_at_k": recall_at_k(ek, ptruth),
+                      "mean_id_overlap_at_k": float(np.mean([len(set(a.tolist()) & set(b.tolist())) / float(k) for a, b in zip(ek, rk)])),
+                      "ground_truth": "raw fp32 exact top-%d of the %d rows (lb200_exact_search_device)" % (k, n_ref)}
+            eidx.close()
+            del Xd
     cpu_note = None
     if world == 1 and not args.no_cpu_baseline and not pq:
         from oracle import reflib

@@ -8,6 +8,8 @@
 // so they agree with the reference to summation-order rounding (1e-5 relative contract) and the
 // returned ids are exact on tie-free data.  Ties are ordered by lower dataset offset.
 #include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <math.h>
 
 #include <type_traits>
@@ -63,8 +65,16 @@ __global__ void __launch_bounds__(kExWarps * 32) exact_block_kernel(const uint8_
                                                                     const uint8_t* __restrict__ queries, uint32_t nq,
                                                                     size_t q_stride, uint32_t row_bytes, uint32_t k,
                                                                     uint32_t rows_per_block, uint64_t* __restrict__ part_keys,
-                                                                    float* __restrict__ part_dists) {
+                                                                    float* __restrict__ part_dists,
+                                                                    const uint8_t* __restrict__ qmask) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
+    if (qmask) { // second pass behind the tensor-core filter (exact_tc.cu): only the queries it could not certify
+        bool any = false;
+        for (uint32_t q = 0; q < kQT; ++q)
+            any |= blockIdx.y * kQT + q < nq && qmask[blockIdx.y * kQT + q];
+        if (!any)
+            return;
+    }
     const uint32_t nchunks = row_bytes / 16;
     uint4* sq = reinterpret_cast<uint4*>(sm_raw);                                // [kQT][nchunks]
     float* sdist = reinterpret_cast<float*>(sm_raw + (size_t)kQT * row_bytes);     // [kQT][kSub]
@@ -152,8 +162,11 @@ __global__ void __launch_bounds__(kExWarps * 32) exact_block_kernel(const uint8_
 // One CTA per query: k-way merge of G ascending lists by repeated arg-min over the list heads.
 // in_*: [G][nq][k]; ties by lower key.  Also the multi-GPU epilogue after the all-gather.
 __global__ void merge_lists_kernel(const uint64_t* __restrict__ in_keys, const float* __restrict__ in_dists, uint32_t G,
-                                   uint32_t nq, uint32_t k, uint64_t* __restrict__ out_keys, float* __restrict__ out_dists) {
+                                   uint32_t nq, uint32_t k, uint64_t* __restrict__ out_keys, float* __restrict__ out_dists,
+                                   const uint8_t* __restrict__ qmask) {
     extern __shared__ uint32_t heads[]; // [G]
+    if (qmask && !qmask[blockIdx.x])
+        return;
     __shared__ float red_d[32];
     __shared__ uint64_t red_k[32];
     __shared__ uint32_t red_g[32];
@@ -253,16 +266,27 @@ template <typename Fn> void dispatch2(int dm, int sk, Fn&& fn) {
 
 } // namespace
 
-void launch_merge_shards(const uint64_t* d_keys, const float* d_dists, size_t shards, size_t nq, size_t k,
-                         uint64_t* d_out_keys, float* d_out_dists, cudaStream_t stream) {
+static void launch_merge_masked(const uint64_t* d_keys, const float* d_dists, size_t shards, size_t nq, size_t k, uint64_t* d_out_keys,
+                                float* d_out_dists, const uint8_t* qmask, cudaStream_t stream) {
     if (!nq || !k)
         return;
     int threads = shards >= 256 ? 256 : (shards >= 64 ? 128 : 32);
     merge_lists_kernel<<<(unsigned)nq, threads, shards * sizeof(uint32_t), stream>>>(
-        d_keys, d_dists, (uint32_t)shards, (uint32_t)nq, (uint32_t)k, d_out_keys, d_out_dists);
+        d_keys, d_dists, (uint32_t)shards, (uint32_t)nq, (uint32_t)k, d_out_keys, d_out_dists, qmask);
     LB_CUDA(cudaGetLastError());
     count_launch();
 }
+
+void launch_merge_shards(const uint64_t* d_keys, const float* d_dists, size_t shards, size_t nq, size_t k,
+                         uint64_t* d_out_keys, float* d_out_dists, cudaStream_t stream) {
+    launch_merge_masked(d_keys, d_dists, shards, nq, k, d_out_keys, d_out_dists, nullptr, stream);
+}
+
+// exact_tc.cu
+bool exact_tc_applicable(int dist_mode, int scalar_kind, size_t n, size_t nq, size_t k, uint32_t row_bytes);
+void launch_exact_tc(int dist_mode, const uint8_t* d_data, size_t n, size_t data_stride, const uint8_t* d_queries, size_t nq,
+                     size_t q_stride, uint32_t row_bytes, size_t k, uint64_t* d_keys, float* d_dists, uint8_t** d_unsafe,
+                     uint32_t** d_unsafe_count, cudaStream_t stream);
 
 void launch_exact(int dist_mode, int scalar_kind, const uint8_t* d_data, size_t n, size_t data_stride,
                   const uint8_t* d_queries, size_t nq, size_t q_stride, uint32_t row_bytes, size_t k, uint64_t* d_keys,
@@ -271,6 +295,13 @@ void launch_exact(int dist_mode, int scalar_kind, const uint8_t* d_data, size_t 
         return;
     if (k > 1024)
         throw CudaError("exact search: count > 1024 is not supported");
+    // f32 l2sq / cos on a GEMM-sized problem: tensor-core filter + exact re-rank (exact_tc.cu); the SIMT kernels below then
+    // run only for the queries the filter could not certify (usually none: every CTA of the second pass exits at once)
+    uint8_t* qmask = nullptr;
+    uint32_t* unsafe_count = nullptr;
+    if (exact_tc_applicable(dist_mode, scalar_kind, n, nq, k, row_bytes))
+        launch_exact_tc(dist_mode, d_data, n, data_stride, d_queries, nq, q_stride, row_bytes, k, d_keys, d_dists, &qmask, &unsafe_count,
+                        stream);
     size_t rows_per_block = 4096;
     if ((n + rows_per_block - 1) / rows_per_block > 1024)
         rows_per_block = round_up((n + 1023) / 1024, kSub);
@@ -286,13 +317,23 @@ void launch_exact(int dist_mode, int scalar_kind, const uint8_t* d_data, size_t 
         auto kern = exact_block_kernel<decltype(dm)::value, decltype(sk)::value>;
         LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kExWarps * 32, smem, stream>>>(d_data, n, data_stride, d_queries, (uint32_t)nq, q_stride, row_bytes,
-                                                    (uint32_t)k, (uint32_t)rows_per_block, part_keys, part_dists);
+                                                    (uint32_t)k, (uint32_t)rows_per_block, part_keys, part_dists, qmask);
         LB_CUDA(cudaGetLastError());
         count_launch();
     });
-    launch_merge_shards(part_keys, part_dists, blocks, nq, k, d_keys, d_dists, stream);
+    launch_merge_masked(part_keys, part_dists, blocks, nq, k, d_keys, d_dists, qmask, stream);
     LB_CUDA(cudaFreeAsync(part_keys, stream));
     LB_CUDA(cudaFreeAsync(part_dists, stream));
+    if (qmask) {
+        if (getenv("LB200_EXACT_REPORT")) { // diagnostics: how many queries needed the SIMT pass
+            uint32_t c = 0;
+            LB_CUDA(cudaMemcpyAsync(&c, unsafe_count, 4, cudaMemcpyDeviceToHost, stream));
+            LB_CUDA(cudaStreamSynchronize(stream));
+            fprintf(stderr, "lb200 exact search: tensor-core filter certified %zu of %zu queries\n", nq - c, nq);
+        }
+        LB_CUDA(cudaFreeAsync(qmask, stream));
+        LB_CUDA(cudaFreeAsync(unsafe_count, stream));
+    }
 }
 
 void launch_pair_distance(int dist_mode, int scalar_kind, const uint8_t* d_a, size_t a_stride, const uint8_t* d_b,

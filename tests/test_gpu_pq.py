@@ -45,6 +45,38 @@ def test_pq_same_graph_same_ids(eng, port, metric):
     assert abs(st["computed_distances"] - tot["computed_distances"]) <= 0.01 * tot["computed_distances"]
 
 
+def test_pq_baseline_geometry_same_graph(eng, port):
+    """BASELINE configs[3] geometry (d = 1536, 96 subvectors x 256 centroids, k = 100 => expansion 100) on a few hundred rows:
+    the oracle builds the PQ graph (compat-128 encoder, decode-then-distance semantics of lantern_storage.hpp:249-270), the
+    engine loads that file and must return the same ids with distances within 1e-5 -- look-up tables of 96 x 128 entries
+    precomputed for the batch, six 16-byte chunks per code row."""
+    rng = np.random.default_rng(21)
+    d, nsub, ncent, n, nq, k = 1536, 96, 256, 700, 64, 100
+    lat = rng.standard_normal((n + nq, 24)).astype(np.float32)
+    P = rng.standard_normal((24, d)).astype(np.float32) / 5
+    V = (lat @ P + 0.1 * rng.standard_normal((n + nq, d))).astype(np.float32)
+    X, Q = V[:n], V[n:]
+    cb = X[rng.choice(n, ncent, replace=False)].copy()  # a valid codebook: 256 corpus rows (per-subvector slices of them)
+    p = port_pq(port, X, cb, nsub, "l2sq", M=8, efc=40, ef=64)
+    g = eng.Index(d, "l2sq", "f32", M=8, efc=40, ef=64, pq=True, num_centroids=ncent, num_subvectors=nsub, codebook=cb)
+    g.load_buffer(p.save_buffer())
+    gk, gd, gc = g.search_batch(Q, k)
+    pk, pd, pc, tot = p.search_batch(Q, k)
+    assert np.array_equal(gc.astype(np.int64), pc)
+    assert np.allclose(gd, pd, rtol=1e-5, atol=1e-5), np.abs(gd - pd).max()
+    assert np.mean(gk == pk) > 0.98, np.mean(gk == pk)
+    st = g.last_stats()
+    assert abs(st["computed_distances"] - tot["computed_distances"]) <= 0.01 * tot["computed_distances"]
+    # and the engine's own batched build at this geometry answers like the oracle-built graph
+    g2 = eng.Index(d, "l2sq", "f32", M=8, efc=40, ef=64, pq=True, num_centroids=ncent, num_subvectors=nsub, codebook=cb)
+    g2.reserve(n)
+    g2.add_batch(np.arange(1, n + 1, dtype=np.uint64), X)
+    g2.build()
+    k2, d2, _ = g2.search_batch(Q, 10)
+    overlap = np.mean([len(set(a.tolist()) & set(b.tolist())) / 10 for a, b in zip(k2, pk[:, :10])])
+    assert overlap > 0.9, overlap
+
+
 def test_pq_exact_order_build_byte_identical_on_integer_data(eng, port):
     """Integer codebook + integer vectors: every distance is an exact small integer on both sides."""
     rng = np.random.default_rng(12)
