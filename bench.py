@@ -49,6 +49,8 @@ WORKLOADS = {
     # (profiles/r01_bench_cfg3_10M_cos.json); the sharded runs match it when --recall-target is not given
     "cfg3": dict(n=10_000_000, dim=768, metric="cos", M=32, efc=128, ef=128, batch=4096, k=10, recall_1gpu=0.88125,
                  desc="cfg3: 10M x d768 f32 cosine, M=32 efc=128 ef=128, batch-4096 k=10"),
+    "cfg3s": dict(n=1_000_000, dim=768, metric="cos", M=32, efc=128, ef=128, batch=4096, k=10,
+                  desc="cfg3s (1/10 scale): 1M x d768 f32 cosine, M=32 efc=128 ef=128, batch-4096 k=10"),
     "cfg4": dict(n=10_000_000, dim=1536, metric="l2sq", M=16, efc=128, ef=64, batch=4096, k=100, pq=(96, 256),
                  desc="cfg4: 10M x d1536 f32 -> PQ 96 subvectors x 256 centroids, l2sq, M=16 efc=128 ef=64 (expansion 100), batch-4096 k=100"),
     "cfg4s": dict(n=1_000_000, dim=1536, metric="l2sq", M=16, efc=128, ef=64, batch=4096, k=100, pq=(96, 256),

@@ -202,9 +202,9 @@ class Index:
             raise EngineError("lb200_init returned NULL")
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and C is not None and _lib is not None:  # (both vanish during interpreter shutdown)
             err = C.c_char_p()
-            lib().lb200_free(self.h, C.byref(err))
+            _lib.lb200_free(self.h, C.byref(err))
             self.h = None
 
     __del__ = close
@@ -336,9 +336,9 @@ class Group:
         return cls(h, world, keep=cb)
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and C is not None and _lib is not None:
             err = C.c_char_p()
-            lib().lb200_group_free(self.h, C.byref(err))
+            _lib.lb200_group_free(self.h, C.byref(err))
             self.h = None
 
     __del__ = close

@@ -108,19 +108,22 @@ template <> __device__ __forceinline__ void accum_chunk<DM_HAMMING, SK_B1>(DistA
 }
 
 // ---- query-side constant (cos: a2 = |q|^2), computed once per query with the same lane layout ------
+// Explicitly rounded operations (no fp contraction left to the compiler): every kernel that folds these chunk sums in the
+// same order (search.cu, group.cu, exact.cu, exact_tc.cu) then produces the SAME bits for |q|^2, which is what makes the
+// multi-GPU group's distances bit-identical to the 1-GPU kernel's.
 template <int DM, int SK> __device__ __forceinline__ float query_norm_chunk(const uint4& q) {
     if constexpr (DM != DM_COS)
         return 0.f;
     else if constexpr (SK == SK_F32) {
         float q0 = __uint_as_float(q.x), q1 = __uint_as_float(q.y), q2 = __uint_as_float(q.z), q3 = __uint_as_float(q.w);
-        return q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
+        return __fmaf_rn(q3, q3, __fmaf_rn(q2, q2, __fmaf_rn(q1, q1, __fmul_rn(q0, q0))));
     } else if constexpr (SK == SK_F16) {
         const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             float2 x = h2f(qw[i]);
-            s += x.x * x.x + x.y * x.y;
+            s = __fmaf_rn(x.y, x.y, __fmaf_rn(x.x, x.x, s));
         }
         return s;
     } else if constexpr (SK == SK_I8) {
@@ -133,6 +136,7 @@ template <int DM, int SK> __device__ __forceinline__ float query_norm_chunk(cons
     } else
         return 0.f;
 }
+__device__ __forceinline__ float norm_add(float acc, float chunk) { return __fadd_rn(acc, chunk); }
 
 __device__ __forceinline__ float cos_from_parts(float ab, float a2, float b2) {
     // index_plugins.hpp:1022-1026

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kExWarps * 32) exact_block_kernel(const uint8_
     if (DM == DM_COS) { // a2 of query `warp`
         float part = 0.f;
         for (uint32_t c = lane; c < nchunks; c += 32)
-            part += query_norm_chunk<DM, SK>(sq[warp * nchunks + c]);
+            part = norm_add(part, query_norm_chunk<DM, SK>(sq[warp * nchunks + c]));
         part = warp_sum(part);
         if (lane == 0)
             sa2[warp] = part;
@@ -239,7 +239,7 @@ __global__ void pair_distance_kernel(const uint8_t* __restrict__ a, size_t a_str
     for (uint32_t c = lane; c < nchunks; c += 32) {
         uint4 qa = __ldg(pa + c), rb = __ldg(pb + c);
         accum_chunk<DM, SK>(acc, qa, rb);
-        part += query_norm_chunk<DM, SK>(qa);
+        part = norm_add(part, query_norm_chunk<DM, SK>(qa));
     }
     float a2 = DM == DM_COS ? warp_sum(part) : 0.f;
     float d = finish_distance<DM, SK>(acc, a2);

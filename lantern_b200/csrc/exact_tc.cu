@@ -450,7 +450,7 @@ template <int DM> __global__ void __launch_bounds__(kRrThreads) exact_tc_rerank_
         if (warp == 0) {
             float part = 0.f;
             for (uint32_t c = lane; c < p.nchunks; c += 32)
-                part += query_norm_chunk<DM, SK_F32>(sq[c]);
+                part = norm_add(part, query_norm_chunk<DM, SK_F32>(sq[c]));
             part = warp_sum(part);
             if (lane == 0)
                 sa2 = part;

@@ -170,7 +170,7 @@ template <int DM, int SK, int NQ> struct GroupWarp {
         for (uint32_t c = lane; c < nchunks; c += 32) {
             const uint4 v = ld_nocache_u4(src + c);
             qs()[c] = v;
-            part += query_norm_chunk<DM, SK>(v);
+            part = norm_add(part, query_norm_chunk<DM, SK>(v));
         }
         a2 = 0.f;
         if constexpr (DM == DM_COS)

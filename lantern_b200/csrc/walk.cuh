@@ -253,7 +253,7 @@ template <int DM, int SK, int NQ> struct RowEval : WalkBase {
         for (int i = 0; i < NQ; ++i) {
             uint32_t c = lane + 32 * i;
             qreg[i] = c < nchunks ? __ldg(qg + c) : make_uint4(0, 0, 0, 0);
-            part += query_norm_chunk<DM, SK>(qreg[i]);
+            part = norm_add(part, query_norm_chunk<DM, SK>(qreg[i]));
         }
         if constexpr (DM == DM_COS)
             a2 = warp_sum(part);
