@@ -238,7 +238,11 @@ LB200_EXPORT void lb200_set_option(lb200_index_t h, char const* name, size_t val
             idx->build_ratio_ = value ? value : 1;
         else if (n == "search_expand")
             idx->search_expand_ = value ? value : 1;
-        else if (n == "touched_cap") // testing knob: size of the per-CTA un-visit log
+        else if (n == "search_kernel") { // 0 = by row width, 1 = one CTA per query, 2 = one warp per query
+            if (value > 2)
+                throw CudaError("search_kernel: 0, 1 or 2");
+            idx->search_kernel_ = value;
+        } else if (n == "touched_cap") // testing knob: size of the per-CTA un-visit log
             idx->touched_cap_ = (uint32_t)std::max<size_t>(value, 32);
         else
             throw CudaError("unknown option");

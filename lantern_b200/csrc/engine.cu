@@ -14,6 +14,9 @@
 
 namespace lb200 {
 
+// rows up to this many bytes are searched by the warp-per-query kernel unless "search_kernel" says otherwise (0: never)
+constexpr size_t kWarpKernelMaxRowBytes = 0;
+
 std::atomic<uint64_t> g_kernel_launches{0};
 
 int device_sm_count() {
@@ -85,7 +88,7 @@ Index::Index(const IndexConfig& cfg, const float* codebook) : cfg_(cfg) {
 Index::~Index() {
     cudaFree(d_vectors_), cudaFree(d_adj0_), cudaFree(d_upper_ref_), cudaFree(d_upper_adj_), cudaFree(d_keys_);
     cudaFree(d_codebook_), cudaFree(scratch_.visited), cudaFree(scratch_.touched), cudaFree(scratch_.counters);
-    cudaFree(d_query_buf_), cudaFree(d_io_buf_);
+    cudaFree(d_query_buf_), cudaFree(d_io_buf_), cudaFree(d_warp_aux_);
     cudaFree(d_pq_pair_), cudaFree(d_pq_norm_), cudaFree(d_pending_raw_), cudaFree(d_pq_tables_);
     if (ev0_)
         cudaEventDestroy(ev0_);
@@ -330,6 +333,17 @@ void Index::search_device(const void* d_queries, size_t nq, size_t stride, int k
     launch_cast_rows(d_queries, stride, kind, qbuf, qrow, cfg_.pq ? (int)SK_F32 : cfg_.scalar_kind, cfg_.dims, nq, stream);
 
     const uint32_t expand = (uint32_t)std::min<size_t>(std::max<size_t>(search_expand_, 1), 8);
+    // kernel choice: one warp per query (no CTA barriers, more queries in flight) for narrow rows, one CTA per query with the
+    // bulk-copy ring for wide rows; "search_kernel" overrides
+    const bool warp_kernel = !cfg_.pq && expand == 1 && cfg_.M0 <= 256 &&
+                             (search_kernel_ == 2 || (search_kernel_ == 0 && row_bytes_ <= kWarpKernelMaxRowBytes));
+    if (warp_kernel) {
+        LB_CUDA(cudaEventRecord(ev0_, stream));
+        launch_warp_search(*this, qbuf, qrow, nq, k, (uint32_t)L, d_keys, d_dists, d_counts, stream);
+        LB_CUDA(cudaEventRecord(ev1_, stream));
+        last_nq_ = (uint32_t)nq;
+        return;
+    }
     GraphView gv = view();
     if (cfg_.pq) {
         // the batch's look-up tables in one dense launch (49 KB per query at 96 x 128): the walk kernel then fetches a table with

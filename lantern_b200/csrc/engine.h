@@ -122,6 +122,9 @@ class Index {
     size_t build_ratio_ = 64;   // a batch never exceeds (visible nodes) / build_ratio_
     uint32_t touched_cap_ = 16384; // per-CTA log of bitmap words to un-visit; beyond it the whole bitmap is cleared
     size_t search_expand_ = 1;  // 1 = exact-order search; 2..4 = relaxed order (see walk.cuh)
+    size_t search_kernel_ = 0;  // 0 = pick by row width, 1 = one CTA per query (search.cu), 2 = one warp per query (group.cu)
+    uint8_t* d_warp_aux_ = nullptr; // warp kernel: counters, flags, dummy counts
+    size_t warp_aux_bytes_ = 0;
     double last_build_ms_ = 0;
     uint64_t last_build_dist_ = 0;
     size_t last_build_n_ = 0;
@@ -201,6 +204,9 @@ struct SearchLaunch {
 };
 uint32_t search_max_ctas(int dist_mode, int scalar_kind, const GraphView& g, uint32_t L, bool pq, uint32_t expand);
 void launch_search(int dist_mode, int scalar_kind, bool pq, const SearchLaunch& p, cudaStream_t stream);
+// group.cu: the warp-per-query kernel as a single-GPU search path
+void launch_warp_search(Index& idx, const uint8_t* qbuf, size_t qrow, size_t nq, size_t k, uint32_t L, uint64_t* d_keys, float* d_dists,
+                        uint32_t* d_counts, cudaStream_t stream);
 // exact.cu
 void launch_exact(int dist_mode, int scalar_kind, const uint8_t* d_data, size_t n, size_t data_stride,
                   const uint8_t* d_queries, size_t nq, size_t q_stride, uint32_t row_bytes, size_t k, uint64_t* d_keys,

@@ -20,6 +20,7 @@
 // all-gather of SURVEY 8e, fused into the search epilogue); a last-warp-out flag exchange makes kernel completion imply
 // that all peers' results have landed.  No NCCL, no host synchronisation on the hot path.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -71,12 +72,14 @@ __device__ __forceinline__ uint4 ld_nocache_u4(const uint4* p) {
 }
 
 struct GroupWarpLayout {
-    uint32_t q, top_d, top_i, cand_id, cand_d, cand_slot, loc, limbo, total;
+    uint32_t ring, bars, top_d, top_i, cand_id, cand_d, cand_slot, loc, limbo, total;
 };
-__host__ __device__ inline GroupWarpLayout group_warp_layout(uint32_t row_bytes, uint32_t L, uint32_t cap) {
+// per warp: R row slots (the bulk-copy ring), R mbarriers, the top list, the candidate arrays
+__host__ __device__ inline GroupWarpLayout group_warp_layout(uint32_t row_bytes, uint32_t R, uint32_t L, uint32_t cap) {
     GroupWarpLayout l;
     uint32_t o = 0;
-    l.q = o, o += (row_bytes + 15u) & ~15u;
+    l.ring = o, o += R * ((row_bytes + 15u) & ~15u);
+    l.bars = o, o += 8 * R;
     l.top_d = o, o += 4 * L;
     l.top_i = o, o += 4 * L;
     l.cand_id = o, o += 4 * cap;
@@ -87,21 +90,32 @@ __host__ __device__ inline GroupWarpLayout group_warp_layout(uint32_t row_bytes,
     l.total = (o + 15u) & ~15u;
     return l;
 }
+// rows in flight per warp: 2 for 3 KB rows, more for narrow rows (about 6 KB of staging per warp)
+inline uint32_t group_ring_slots(uint32_t row_bytes) {
+    uint32_t r = 6144u / row_bytes;
+    return r < 2 ? 2 : (r > 8 ? 8 : r);
+}
 
 // ---- one warp = one query slot -------------------------------------------------------------------------------------
-// Header payloads of the owner -> helper mailbox: a count (1..cap) announces that many ids; kMsgStart | q opens query q
-// (the helper loads it into shared memory); kMsgExit ends the launch for this slot.
-constexpr uint32_t kMsgStart = 0x80000000u;
+// Header payload of the owner -> helper mailbox: count (bits 0-8, 1..256 ids follow) | query index << 9, or kMsgExit (the
+// launch is over for this slot).  The query index travels with EVERY request -- the header is a single word that the next
+// message overwrites, so a separate "start of query" message could be lost before the helper had seen it; the helper loads a
+// query into shared memory when the index in a request differs from the one it holds.
 constexpr uint32_t kMsgExit = 0xFFFFFFFFu;
+constexpr uint32_t kMsgCountBits = 9;
+constexpr size_t kGroupMaxBatch = (size_t)1 << (32 - kMsgCountBits - 1);
 
 template <int DM, int SK, int NQ> struct GroupWarp {
     const GroupLaunch& p;
     int lane;
     uint32_t slot, nchunks;
     uint8_t* ws; // this warp's shared memory
+    uint4 qreg[NQ]; // the query, in registers (lane l holds chunks l, l+32, ...)
+    uint32_t phase_bits; // parity of each ring slot's mbarrier
     float a2;
-    uint32_t seq;  // owner: messages sent by this slot in this launch
-    uint32_t last; // helper: flag of the last header seen
+    uint32_t seq;   // owner: messages sent by this slot in this launch
+    uint32_t last;  // helper: flag of the last header seen
+    uint32_t cur_q; // the query this slot holds in shared memory (0xFFFFFFFF: none)
     bool dead, waited;
     unsigned long long t0;
     uint32_t st_dist, st_pops, st_hops, st_rounds, st_rows;
@@ -109,8 +123,9 @@ template <int DM, int SK, int NQ> struct GroupWarp {
     __device__ __forceinline__ explicit GroupWarp(const GroupLaunch& gp) : p(gp) {}
 
     // shared-memory arrays are addressed from one base (fewer live registers than eight pointers)
-    __device__ __forceinline__ GroupWarpLayout lay() const { return group_warp_layout(p.g.row_bytes, p.L, p.cap); }
-    __device__ __forceinline__ uint4* qs() const { return reinterpret_cast<uint4*>(ws); }
+    __device__ __forceinline__ GroupWarpLayout lay() const { return group_warp_layout(p.g.row_bytes, p.ring_slots, p.L, p.cap); }
+    __device__ __forceinline__ uint8_t* ring() const { return ws; }
+    __device__ __forceinline__ uint64_t* bars() const { return reinterpret_cast<uint64_t*>(ws + lay().bars); }
     __device__ __forceinline__ float* top_d() const { return reinterpret_cast<float*>(ws + lay().top_d); }
     __device__ __forceinline__ uint32_t* top_i() const { return reinterpret_cast<uint32_t*>(ws + lay().top_i); }
     __device__ __forceinline__ uint32_t* cand_id() const { return reinterpret_cast<uint32_t*>(ws + lay().cand_id); }
@@ -167,38 +182,57 @@ template <int DM, int SK, int NQ> struct GroupWarp {
         wait_queries();
         const uint4* src = reinterpret_cast<const uint4*>(p.queries + (size_t)q * p.query_stride);
         float part = 0.f;
-        for (uint32_t c = lane; c < nchunks; c += 32) {
-            const uint4 v = ld_nocache_u4(src + c);
-            qs()[c] = v;
-            part = norm_add(part, query_norm_chunk<DM, SK>(v));
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            const uint32_t c = lane + 32 * i;
+            qreg[i] = c < nchunks ? ld_nocache_u4(src + c) : make_uint4(0, 0, 0, 0);
+            part = norm_add(part, query_norm_chunk<DM, SK>(qreg[i]));
         }
         a2 = 0.f;
         if constexpr (DM == DM_COS)
             a2 = warp_sum(part);
-        __syncwarp();
     }
 
-    // distance query -> one local row (all loads of the row are issued before the first use).  Lane layout and reduction order
-    // are those of RowEval::row_distance (walk.cuh), so the value is bit-identical to the 1-GPU kernel's.
-    __device__ __forceinline__ float dist1(uint32_t id) const {
-        const uint4* ra = reinterpret_cast<const uint4*>(p.g.vectors + (size_t)(id - p.bounds[p.me]) * p.g.row_bytes);
-        uint4 va[NQ];
+    // ---- distances query -> a list of LOCAL rows, through this warp's bulk-copy ring (cp.async.bulk + mbarrier, as
+    // RowEval in walk.cuh but private to the warp): ring_slots rows are in flight at once, a slot is refilled as soon as it
+    // has been read.  OWNER: entry t of the list is candidate loc[t]; helper: entry t is cand_id[t].  Lane layout and
+    // reduction order are RowEval::row_distance's, so every value is bit-identical to the 1-GPU kernel's.
+    __device__ __forceinline__ void issue_row(uint32_t s, uint32_t id) {
+        uint64_t* bar = bars() + s;
+        mbar_arrive_expect_tx(bar, p.g.row_bytes);
+        bulk_g2s(ring() + (size_t)s * p.g.row_bytes, p.g.vectors + (size_t)(id - p.bounds[p.me]) * p.g.row_bytes, p.g.row_bytes, bar);
+    }
+    template <bool OWNER> __device__ __forceinline__ void eval_local(uint32_t n) {
+        const uint32_t R = p.ring_slots;
+        const uint32_t* ids = cand_id();
+        const uint8_t* lj = loc();
+        if ((uint32_t)lane < min(n, R))
+            issue_row(lane, ids[OWNER ? lj[lane] : lane]);
+        uint32_t s = 0;
+#pragma unroll 1
+        for (uint32_t t = 0; t < n; ++t) {
+            mbar_wait(bars() + s, (phase_bits >> s) & 1u);
+            phase_bits ^= 1u << s;
+            const uint4* row = reinterpret_cast<const uint4*>(ring() + (size_t)s * p.g.row_bytes);
+            DistAcc<DM, SK> acc;
+            acc.reset();
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-            const uint32_t c = lane + 32 * i;
-            if (c < nchunks)
-                va[i] = __ldg(ra + c);
+            for (int i = 0; i < NQ; ++i) {
+                const uint32_t c = lane + 32 * i;
+                if (c < nchunks)
+                    accum_chunk<DM, SK>(acc, qreg[i], row[c]);
+            }
+            const float d = finish_distance<DM, SK>(acc, a2);
+            if (lane == 0)
+                cand_d()[OWNER ? lj[t] : t] = d;
+            __syncwarp();
+            if (t + R < n && lane == 0) {
+                fence_proxy_async(); // our generic-proxy reads of the slot precede the async refill
+                issue_row(s, ids[OWNER ? lj[t + R] : t + R]);
+            }
+            s = (s + 1 == R) ? 0 : s + 1;
         }
-        DistAcc<DM, SK> acc;
-        acc.reset();
-        const uint4* q4 = qs();
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-            const uint32_t c = lane + 32 * i;
-            if (c < nchunks)
-                accum_chunk<DM, SK>(acc, q4[c], va[i]);
-        }
-        return finish_distance<DM, SK>(acc, a2);
+        st_rows += n;
     }
 
     // ---- owner: distances query -> cand_id[0..n) into cand_d[0..n), each evaluated where the row lives -----------
@@ -237,17 +271,10 @@ template <int DM, int SK, int NQ> struct GroupWarp {
             }
         }
         if ((uint32_t)lane < G && (uint32_t)lane != me && cnt)
-            st_sys_u64(p.req[lane] + (size_t)slot * (1 + cap), pack_word(cnt, flag));
+            st_sys_u64(p.req[lane] + (size_t)slot * (1 + cap), pack_word(cnt | (cur_q << kMsgCountBits), flag));
         const uint32_t nloc = __shfl_sync(0xffffffffu, cnt, me);
         __syncwarp();
-#pragma unroll 1
-        for (uint32_t t = 0; t < nloc; ++t) {
-            const uint32_t j = loc()[t];
-            const float d = dist1(cand_id()[j]);
-            if (lane == 0)
-                cand_d()[j] = d;
-        }
-        st_rows += nloc;
+        eval_local<true>(nloc);
         const unsigned long long* inbox = p.resp[me] + (size_t)slot * G * cap;
 #pragma unroll 1
         for (uint32_t base = 0; base < n; base += 32) {
@@ -294,11 +321,13 @@ template <int DM, int SK, int NQ> struct GroupWarp {
             last = flag;
             if (n_d == kMsgExit)
                 return;
-            if (n_d & kMsgStart) {
-                load_query(n_d & ~kMsgStart);
+            const uint32_t q = n_d >> kMsgCountBits;
+            n_d &= (1u << kMsgCountBits) - 1u;
+            if (q != cur_q) {
+                load_query(q);
+                cur_q = q;
                 if (dead)
                     return;
-                continue;
             }
 #pragma unroll 1
             for (uint32_t base = 0; base < n_d; base += 32) {
@@ -307,17 +336,15 @@ template <int DM, int SK, int NQ> struct GroupWarp {
                 dead = __any_sync(0xffffffffu, dead);
                 if (dead)
                     return;
-                float my_d = 0.f;
-#pragma unroll 1
-                for (uint32_t t = 0; t < cnt; ++t) {
-                    const float d = dist1(__shfl_sync(0xffffffffu, my_id, t));
-                    if ((uint32_t)lane == t)
-                        my_d = d;
-                }
+                if ((uint32_t)lane < cnt)
+                    cand_id()[lane] = my_id;
+                __syncwarp();
+                eval_local<false>(cnt);
+                __syncwarp();
+                const float my_d = (uint32_t)lane < cnt ? cand_d()[lane] : 0.f;
                 if ((uint32_t)lane < cnt)
                     st_sys_u64(outbox + base + lane, pack_word(__float_as_uint(my_d), flag));
             }
-            st_rows += n_d;
         }
     }
 
@@ -334,8 +361,8 @@ template <int DM, int SK, int NQ> struct GroupWarp {
         const uint32_t M0 = p.g.M0, L = p.L;
         uint32_t* vis = p.vis + (size_t)(slot / p.G) * p.words_per_slot;
         uint32_t* touched = p.touched + (size_t)(slot / p.G) * p.touched_cap;
-        tell_helpers(kMsgStart | q);
         load_query(q);
+        cur_q = q;
         int level = -1; // -1: measuring the entry point; >= 1: greedy on that level; 0: beam on the base layer
         uint32_t cur = p.g.entry;
         float cur_d = 0.f;
@@ -510,15 +537,22 @@ template <int DM, int SK, int NQ> struct GroupWarp {
 };
 
 template <int DM, int SK, int NQ>
-__global__ void __launch_bounds__(kGroupThreads, 7) group_search_kernel(const __grid_constant__ GroupLaunch p) {
+__global__ void __launch_bounds__(kGroupThreads, 6) group_search_kernel(const __grid_constant__ GroupLaunch p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     GroupWarp<DM, SK, NQ> w(p);
     w.lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     w.slot = blockIdx.x * kGroupWarps + warp;
     w.nchunks = p.g.row_bytes / 16;
-    w.ws = smem_raw + (size_t)warp * group_warp_layout(p.g.row_bytes, p.L, p.cap).total;
-    w.seq = 0, w.last = p.flag_base, w.dead = false, w.a2 = 0.f;
+    w.ws = smem_raw + (size_t)warp * group_warp_layout(p.g.row_bytes, p.ring_slots, p.L, p.cap).total;
+    w.phase_bits = 0;
+    if (w.lane == 0) {
+        for (uint32_t i = 0; i < p.ring_slots; ++i)
+            mbar_init(w.bars() + i, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    w.seq = 0, w.last = p.flag_base, w.dead = false, w.a2 = 0.f, w.cur_q = 0xFFFFFFFFu;
     w.waited = (p.me == p.root);
     w.st_dist = w.st_pops = w.st_hops = w.st_rounds = w.st_rows = 0;
     w.t0 = globaltimer_ns();
@@ -587,6 +621,26 @@ template <int DM, int SK, int NQ> int group_occupancy_one(size_t smem) {
     return blocks;
 }
 
+// in-degree of the base layer per bucket of consecutive rows: how often the rows of a bucket appear in adjacency lists is
+// how often they will be measured.  Row ranges of equal WEIGHT (not equal length) balance the ranks: early rows of an HNSW
+// build collect more links than late ones, so equal-length ranges would leave the first rank with ~40 % more work.
+constexpr uint32_t kBalanceBuckets = 4096;
+__global__ void indegree_hist_kernel(const uint32_t* __restrict__ adj0, size_t total, uint32_t n, unsigned long long* __restrict__ hist) {
+    __shared__ uint32_t sh[kBalanceBuckets];
+    for (uint32_t i = threadIdx.x; i < kBalanceBuckets; i += blockDim.x)
+        sh[i] = 0;
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t id = adj0[i];
+        if (id < n)
+            atomicAdd(&sh[(uint32_t)(((unsigned long long)id * kBalanceBuckets) / n)], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kBalanceBuckets; i += blockDim.x)
+        if (sh[i])
+            atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
 __global__ void group_copy_results_kernel(const uint64_t* __restrict__ rk, const float* __restrict__ rd, const uint32_t* __restrict__ rc,
                                           uint64_t* __restrict__ keys, float* __restrict__ dists, uint32_t* __restrict__ counts,
                                           size_t nq, size_t k) {
@@ -607,6 +661,12 @@ __global__ void group_copy_results_kernel(const uint64_t* __restrict__ rk, const
 // host side
 // =====================================================================================================================
 
+struct DeviceGuard { // the group switches devices; the caller's current device is put back when an entry point returns
+    int dev = 0;
+    DeviceGuard() { cudaGetDevice(&dev); }
+    ~DeviceGuard() { cudaSetDevice(dev); }
+};
+
 struct PtrBlob { // how one device allocation is handed to the other ranks
     cudaIpcMemHandle_t ipc;
     void* raw;
@@ -619,6 +679,7 @@ struct GroupConfigBlob {
     uint32_t entry;
     int32_t max_level;
     uint32_t flags;
+    uint32_t bounds[kGroupMax + 1]; // row ranges, balanced by base-layer in-degree
     PtrBlob vectors, adj0, upper_ref, upper_adj, keys;
 };
 
@@ -736,6 +797,39 @@ class GroupRank {
         c.n = idx->n_, c.upper_lists = idx->upper_lists_, c.row_bytes = idx->row_bytes_, c.vec_bytes = idx->vec_bytes_;
         c.entry = idx->entry_, c.max_level = idx->max_level_;
         c.flags = idx->view().flags;
+        { // contiguous row ranges of equal expected work
+            unsigned long long* d_hist = nullptr;
+            LB_CUDA(cudaMalloc(&d_hist, kBalanceBuckets * sizeof(unsigned long long)));
+            LB_CUDA(cudaMemset(d_hist, 0, kBalanceBuckets * sizeof(unsigned long long)));
+            indegree_hist_kernel<<<1024, 256>>>(idx->d_adj0_, (size_t)idx->n_ * idx->cfg_.M0, (uint32_t)idx->n_, d_hist);
+            LB_CUDA(cudaGetLastError());
+            count_launch();
+            std::vector<unsigned long long> hist(kBalanceBuckets);
+            LB_CUDA(cudaMemcpy(hist.data(), d_hist, hist.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            LB_CUDA(cudaFree(d_hist));
+            double total = 0;
+            for (unsigned long long h : hist)
+                total += (double)h + 1.0; // + 1: rows nobody links to still have to live somewhere
+            const size_t n_rows = idx->n_;
+            c.bounds[0] = 0;
+            double acc = 0;
+            int r = 1;
+            for (uint32_t b = 0; b < kBalanceBuckets && r < world; ++b) {
+                acc += (double)hist[b] + 1.0;
+                while (r < world && acc >= total * r / world) {
+                    c.bounds[r] = (uint32_t)std::min<size_t>(n_rows, ((size_t)(b + 1) * n_rows + kBalanceBuckets - 1) / kBalanceBuckets);
+                    ++r;
+                }
+            }
+            for (; r <= world; ++r)
+                c.bounds[r] = (uint32_t)n_rows;
+            c.bounds[world] = (uint32_t)n_rows;
+            if (getenv("LB200_GROUP_EQUAL_RANGES")) // experiments: plain n*r/G ranges
+                for (int q = 0; q <= world; ++q)
+                    c.bounds[q] = (uint32_t)((n_rows * (size_t)q) / (size_t)world);
+            for (int q = 1; q <= world; ++q) // monotone, whatever the histogram looked like
+                c.bounds[q] = std::max(c.bounds[q], c.bounds[q - 1]);
+        }
         c.vectors = export_ptr(idx->d_vectors_), c.adj0 = export_ptr(idx->d_adj0_);
         c.upper_ref = export_ptr(idx->d_upper_ref_), c.upper_adj = export_ptr(idx->d_upper_adj_);
         c.keys = export_ptr(idx->d_keys_);
@@ -755,7 +849,7 @@ class GroupRank {
         if (cfg.M0 > 256)
             throw CudaError("group: connectivity above 128 is not supported");
         for (int r = 0; r <= world; ++r)
-            bounds[r] = (uint32_t)((n * (size_t)r) / (size_t)world); // contiguous row ranges
+            bounds[r] = c.bounds[r]; // contiguous row ranges, sized by the root for equal expected work
         const size_t lo = bounds[rank], hi = bounds[rank + 1];
         LB_CUDA(cudaMalloc(&d_rows, std::max<size_t>((hi - lo) * row_bytes, 16)));
         LB_CUDA(cudaMalloc(&d_adj0, n * cfg.M0 * 4));
@@ -805,7 +899,7 @@ class GroupRank {
 
     int occupancy_for(uint32_t L) {
         LB_CUDA(cudaSetDevice(device));
-        const size_t smem = (size_t)group_warp_layout((uint32_t)row_bytes, L, cap).total * kGroupWarps;
+        const size_t smem = (size_t)group_warp_layout((uint32_t)row_bytes, group_ring_slots((uint32_t)row_bytes), L, cap).total * kGroupWarps;
         const int nq = pick_nq((uint32_t)row_bytes);
         if (nq < 0)
             throw CudaError("group: vectors wider than 8192 bytes are not supported");
@@ -826,6 +920,8 @@ class GroupRank {
         LB_CUDA(cudaSetDevice(device));
         if (nq > max_batch || nq * k > res_cap)
             throw CudaError("group: batch larger than the group was created for (max_batch / max_results)");
+        if (nq >= kGroupMaxBatch)
+            throw CudaError("group: more than 4 M queries per batch");
         if (rank == root) {
             if (!d_queries)
                 throw CudaError("group: the root rank must pass the queries");
@@ -834,7 +930,7 @@ class GroupRank {
         ++epoch; // callers run renew_flags() first: (epoch & 0xFFF) is never 0 here
         GroupLaunch p;
         memset(&p, 0, sizeof(p));
-        p.G = (uint32_t)world, p.me = (uint32_t)rank, p.W = W, p.cap = cap;
+        p.G = (uint32_t)world, p.me = (uint32_t)rank, p.W = W, p.cap = cap, p.ring_slots = group_ring_slots((uint32_t)row_bytes);
         p.nq = (uint32_t)nq, p.k = (uint32_t)k, p.L = L;
         p.flag_base = (epoch & 0xFFFu) << 20;
         p.epoch = epoch, p.root = (uint32_t)root;
@@ -858,7 +954,7 @@ class GroupRank {
         p.vis = d_vis, p.touched = d_touched, p.words_per_slot = words_per_slot, p.touched_cap = touched_cap;
         p.counters = d_counters;
         LB_CUDA(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned long long), stream));
-        const size_t smem = (size_t)group_warp_layout((uint32_t)row_bytes, L, cap).total * kGroupWarps;
+        const size_t smem = (size_t)group_warp_layout((uint32_t)row_bytes, group_ring_slots((uint32_t)row_bytes), L, cap).total * kGroupWarps;
         const uint32_t slots = (uint32_t)std::min<size_t>(W, round_up(nq, (size_t)world)); // W and nq rounded up are multiples of G
         const uint32_t grid = (slots + kGroupWarps - 1) / kGroupWarps;
         p.W = W;
@@ -959,6 +1055,7 @@ static uint32_t agree_W(Group& G, uint32_t L) {
 }
 
 void group_distribute(Group& G, Index* root_index, int root, size_t max_batch, size_t max_results) {
+    DeviceGuard dg;
     std::lock_guard<std::mutex> lk(G.mu);
     if (G.distributed)
         throw CudaError("group: already distributed");
@@ -1028,6 +1125,7 @@ static uint32_t beam_width(const GroupRank& r, size_t k, size_t ef) {
 
 void group_search_device(Group& G, const void* d_queries, size_t nq, size_t stride, int kind, size_t k, size_t ef,
                          uint64_t* d_keys, float* d_dists, uint32_t* d_counts, cudaStream_t stream) {
+    DeviceGuard dg;
     std::lock_guard<std::mutex> lk(G.mu);
     if (!G.distributed)
         throw CudaError("group: lb200_group_distribute has not been called");
@@ -1045,6 +1143,7 @@ void group_search_device(Group& G, const void* d_queries, size_t nq, size_t stri
 // host buffers: queries are read on the root rank only; every rank receives the results
 void group_search_host(Group& G, const void* queries, size_t nq, size_t stride, int kind, size_t k, size_t ef, uint64_t* keys,
                        float* dists, size_t* counts) {
+    DeviceGuard dg;
     std::lock_guard<std::mutex> lk(G.mu);
     if (!G.distributed)
         throw CudaError("group: lb200_group_distribute has not been called");
@@ -1106,6 +1205,7 @@ void group_search_host(Group& G, const void* queries, size_t nq, size_t stride, 
 }
 
 void group_stats(Group& G, int which, GroupStats& out) {
+    DeviceGuard dg;
     std::lock_guard<std::mutex> lk(G.mu);
     if (which < 0 || (size_t)which >= G.ranks.size())
         throw CudaError("group: no such local rank");
@@ -1148,6 +1248,7 @@ Group* group_create_local(const int* devices, int ndev) {
     if (ndev < 1 || ndev > kGroupMax)
         throw CudaError("group: 1..8 devices");
     require_device();
+    DeviceGuard dg;
     int have = 0;
     LB_CUDA(cudaGetDeviceCount(&have));
     Group* G = new Group();
@@ -1183,7 +1284,68 @@ Group* group_create_local(const int* devices, int ndev) {
     return G;
 }
 
-void group_free(Group* G) { delete G; }
+// ---- the same kernel as a single-GPU search path: G = 1, every slot is an owner, nothing crosses NVLink ------------------
+// One warp per query instead of one CTA per query (search.cu): no CTA-wide barriers, 28 queries in flight per SM instead of
+// 8-10.  For narrow rows (binary vectors, short f16/i8 rows) the per-expansion serial chain of the CTA kernel -- warp 0
+// working while three warps wait at the barrier -- is what bounds it; here every warp always has its own work.
+void launch_warp_search(Index& idx, const uint8_t* qbuf, size_t qrow, size_t nq, size_t k, uint32_t L, uint64_t* d_keys, float* d_dists,
+                        uint32_t* d_counts, cudaStream_t stream) {
+    const IndexConfig& cfg = idx.cfg_;
+    if (cfg.pq)
+        throw CudaError("warp search: pq indexes use the CTA kernel");
+    const uint32_t cap = (uint32_t)cfg.M0;
+    if (cap > 256)
+        throw CudaError("warp search: connectivity above 128 is not supported");
+    const int nqc = pick_nq((uint32_t)idx.row_bytes_);
+    const size_t smem = (size_t)group_warp_layout((uint32_t)idx.row_bytes_, group_ring_slots((uint32_t)idx.row_bytes_), L, cap).total * kGroupWarps;
+    int occ = 0;
+    dispatch_walk(idx.dist_mode_, cfg.scalar_kind, nqc, [&](auto d, auto s2, auto q) {
+        occ = group_occupancy_one<decltype(d)::value, decltype(s2)::value, decltype(q)::value>(smem);
+    });
+    if (occ < 1)
+        throw CudaError("warp search: kernel does not fit on an SM (ef too large for shared memory)");
+    const uint32_t W = (uint32_t)occ * (uint32_t)device_sm_count() * kGroupWarps;
+    idx.ensure_scratch(W); // one visited bitmap + touched list per slot
+    const size_t aux_need = 256 + round_up(nq * 4, 256);
+    if (aux_need > idx.warp_aux_bytes_) {
+        if (idx.d_warp_aux_)
+            LB_CUDA(cudaFree(idx.d_warp_aux_));
+        idx.d_warp_aux_ = nullptr;
+        idx.warp_aux_bytes_ = aux_need + aux_need / 2;
+        LB_CUDA(cudaMalloc(&idx.d_warp_aux_, idx.warp_aux_bytes_));
+    }
+    uint8_t* aux = idx.d_warp_aux_;
+    LB_CUDA(cudaMemsetAsync(aux, 0, 256, stream)); // [0,64) counters, [64,72) done, [72,80) qready, [80,84) err
+    GroupLaunch p;
+    memset(&p, 0, sizeof(p));
+    p.G = 1, p.me = 0, p.W = W, p.cap = cap, p.ring_slots = group_ring_slots((uint32_t)idx.row_bytes_);
+    p.nq = (uint32_t)nq, p.k = (uint32_t)k, p.L = L;
+    p.flag_base = 1u << 20, p.epoch = 1, p.root = 0;
+    p.timeout_ns = ~0ull;
+    p.g = idx.view();
+    p.bounds[0] = 0;
+    for (int r = 1; r <= kGroupMax; ++r)
+        p.bounds[r] = 0xFFFFFFFFu;
+    p.res_keys[0] = d_keys, p.res_dists[0] = d_dists;
+    p.res_counts[0] = d_counts ? d_counts : (uint32_t*)(aux + 256);
+    p.counters = (unsigned long long*)aux;
+    p.done[0] = (unsigned long long*)(aux + 64), p.qready[0] = (unsigned long long*)(aux + 72), p.err[0] = (uint32_t*)(aux + 80);
+    p.queries = qbuf, p.query_stride = (uint32_t)qrow;
+    p.vis = idx.scratch_.visited, p.touched = idx.scratch_.touched;
+    p.words_per_slot = idx.scratch_.words_per_cta, p.touched_cap = idx.scratch_.touched_cap;
+    const uint32_t slots = (uint32_t)std::min<size_t>(W, round_up(nq, kGroupWarps));
+    const uint32_t grid = (slots + kGroupWarps - 1) / kGroupWarps;
+    dispatch_walk(idx.dist_mode_, cfg.scalar_kind, nqc, [&](auto d, auto s2, auto q) {
+        group_launch_one<decltype(d)::value, decltype(s2)::value, decltype(q)::value>(p, grid, smem, stream);
+    });
+    // work counters where Index::last_stats() reads them: [1] distance evaluations, [2] base pops, [3] upper hops
+    LB_CUDA(cudaMemcpyAsync(idx.scratch_.counters + 1, p.counters + 1, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
+}
+
+void group_free(Group* G) {
+    DeviceGuard dg;
+    delete G;
+}
 int group_world(const Group& G) { return G.world; }
 int group_local_ranks(const Group& G) { return (int)G.ranks.size(); }
 

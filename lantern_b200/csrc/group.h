@@ -13,6 +13,7 @@ constexpr int kGroupMax = 8;
 // kernel parameters of group_search_kernel (identical on every rank except `me`, the local pointers and the peer views)
 struct GroupLaunch {
     uint32_t G, me, W, cap; // ranks, this rank, query slots (= resident warps) per GPU, ids per message (= M0)
+    uint32_t ring_slots;    // rows a warp keeps in flight (its private bulk-copy ring)
     uint32_t nq, k, L;
     uint32_t flag_base; // message flags of this launch are flag_base + 1, +2, ...
     uint32_t epoch, root;

@@ -18,12 +18,18 @@ B = int(sys.argv[4]) if len(sys.argv) > 4 else 4096
 dim, k, ef, M = 768, 10, 128 if metric == "cos" else 64, 32 if metric == "cos" else 16
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
-X = bench.structured_torch(n, dim, 42, dev)
-Q = bench.structured_torch(4 * B, dim, 43, dev).cpu().numpy()
-idx = api.Index(dim, metric, "f32", M=M, efc=128, ef=ef)
+kind, rowb = "f32", dim * 4
+if metric == "hamming":  # cfg5-like: 768-byte binary rows
+    dim, kind, rowb = 6144, "b1", 768
+    X = bench.bits_torch(n, dim, 42, dev)
+    Q = bench.bits_torch(4 * B, dim, 43, dev).cpu().numpy()
+else:
+    X = bench.structured_torch(n, dim, 42, dev)
+    Q = bench.structured_torch(4 * B, dim, 43, dev).cpu().numpy()
+idx = api.Index(dim, metric, kind, M=M, efc=128, ef=ef)
 idx.reserve(n)
 t0 = time.perf_counter()
-idx.add_batch_device(np.arange(1, n + 1, dtype=np.uint64), X.data_ptr(), n, dim * 4, "f32")
+idx.add_batch_device(np.arange(1, n + 1, dtype=np.uint64), X.data_ptr(), n, rowb, kind)
 idx.build()
 torch.cuda.synchronize()
 print("build %.1f s" % (time.perf_counter() - t0), idx.last_build_stats(), flush=True)
@@ -32,7 +38,17 @@ st1 = idx.last_stats()
 for _ in range(3):
     idx.search_batch(Q[:B], k, ef)
 st1 = idx.last_stats()
-print("1 GPU kernel: %.3f ms  %.0f q/s  evals/q %.0f" % (st1["kernel_ms"], B / st1["kernel_ms"] * 1e3, st1["computed_distances"] / B), flush=True)
+print("1 GPU kernel (one CTA per query): %.3f ms  %.0f q/s  evals/q %.0f  alg GB/s %.0f" % (
+    st1["kernel_ms"], B / st1["kernel_ms"] * 1e3, st1["computed_distances"] / B, st1["algorithmic_bytes"] / st1["kernel_ms"] / 1e6), flush=True)
+idx.set_option("search_kernel", 2)
+kw, dw, cw = idx.search_batch(Q[:B], k, ef)
+for _ in range(3):
+    idx.search_batch(Q[:B], k, ef)
+stw = idx.last_stats()
+print("1 GPU kernel (one warp per query): %.3f ms  %.0f q/s  identical rows %.4f  bit-equal dists %s  same counters %s  alg GB/s %.0f" % (
+    stw["kernel_ms"], B / stw["kernel_ms"] * 1e3, float(np.mean(np.all(kw == k1, axis=1))), np.array_equal(dw.view(np.uint32), d1.view(np.uint32)),
+    stw["computed_distances"] == st1["computed_distances"], stw["algorithmic_bytes"] / stw["kernel_ms"] / 1e6), flush=True)
+idx.set_option("search_kernel", 1)
 ndev = api.device_count()
 for rk in sorted(set([1, ranks])):
     grp = api.Group.local([r % ndev for r in range(rk)])

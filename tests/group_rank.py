@@ -59,7 +59,7 @@ assert np.array_equal(dk.cpu().numpy().astype(np.uint64), k1) and np.array_equal
 evals = [None] * world
 dist.all_gather_object(evals, (st["owner_computed_distances"], st["local_rows_evaluated"]))
 assert sum(e[0] for e in evals) == total and sum(e[1] for e in evals) == total - nq, (evals, total)
-assert st["local_rows_evaluated"] > 0 and st["rows_held"] in (n // world, n // world + 1)
+assert st["local_rows_evaluated"] > 0 and 0 < st["rows_held"] < n
 print("group rank ok %d/%d: %d local rows evaluated, kernel %.3f ms" % (rank, world, st["local_rows_evaluated"], st["kernel_ms"]))
 grp.close()
 dist.destroy_process_group()

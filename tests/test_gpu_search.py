@@ -189,3 +189,32 @@ def test_high_connectivity_graph(eng, port):
     gk, gd, _ = g.search_batch(Q, 20)
     pk, pd, _, _ = pidx.search_batch(Q, 20)
     assert np.allclose(gd, pd, rtol=1e-5, atol=1e-6) and np.mean(gk == pk) > 0.99
+
+
+@pytest.mark.parametrize("metric,quant,d", [("l2sq", "f32", 64), ("cos", "f32", 768), ("hamming", "b1", 6144), ("cos", "i8", 80), ("l2sq", "f16", 128)])
+def test_warp_per_query_kernel_equals_cta_kernel(eng, metric, quant, d):
+    """The one-warp-per-query search kernel (csrc/group.cu with one rank; the narrow-row path and the multi-GPU kernel) against
+    the one-CTA-per-query kernel (csrc/search.cu) on the same graph: same ids, bit-identical distances, same work counters."""
+    rng = np.random.default_rng(4)
+    n = 4000
+    if quant == "b1":
+        protos = rng.integers(0, 256, (16, d // 8), dtype=np.uint8)
+        X = protos[rng.integers(0, 16, n)] ^ np.packbits(rng.random((n, d)) < 0.1, axis=1)
+        Q = protos[rng.integers(0, 16, 200)] ^ np.packbits(rng.random((200, d)) < 0.1, axis=1)
+    else:
+        X, Q = structured(n, d, seed=7), structured(200, d, seed=8)
+        if quant == "i8":
+            X, Q = X * 0.3, Q * 0.3
+    g = eng.Index(d, metric, quant, M=16, efc=64, ef=48)
+    g.reserve(n)
+    g.add_batch(np.arange(1, n + 1, dtype=np.uint64), X)
+    g.build()
+    for k, ef in ((10, 48), (100, 300), (1, 1)):
+        g.set_option("search_kernel", 1)
+        k1, d1, c1 = g.search_batch(Q, k, ef)
+        s1 = g.last_stats()
+        g.set_option("search_kernel", 2)
+        k2, d2, c2 = g.search_batch(Q, k, ef)
+        s2 = g.last_stats()
+        assert np.array_equal(k1, k2) and np.array_equal(d1.view(np.uint32), d2.view(np.uint32)) and np.array_equal(c1, c2)
+        assert (s1["computed_distances"], s1["base_pops"], s1["upper_hops"]) == (s2["computed_distances"], s2["base_pops"], s2["upper_hops"])
