@@ -942,7 +942,10 @@ def run_group(args, wl):
             idx.search_batch_device(Q[(s_ % pool) * B].data_ptr(), B, rowb, kind, k, ef, k1.data_ptr(), d1.data_ptr(), 0, stream.cuda_stream)
         e1.record(stream)
         torch.cuda.synchronize()
-        one_gpu = {"value": reps * B / (e0.elapsed_time(e1) / 1e3), "unit": "queries/s", "recall_at_k": rec,
+        idx.search_batch_device(Q.data_ptr(), B, rowb, kind, k, ef, k1.data_ptr(), d1.data_ptr(), 0, stream.cuda_stream)
+        torch.cuda.synchronize()
+        one_gpu = {"value": reps * B / (e0.elapsed_time(e1) / 1e3), "unit": "queries/s",
+                   "recall_at_k": recall_at_k(k1[:nrec].cpu().numpy(), truth),
                    "what": "lb200_search_batch_device on rank 0's unsharded copy of the same graph, %d steps" % reps}
     for s in range(args.warmup):
         step_device(s)

@@ -300,6 +300,9 @@ LB200_EXPORT void lb200_group_search_batch_device(lb200_group_t, void const* d_q
                                                   lb200_scalar_kind_t query_kind, size_t count, size_t ef,
                                                   lb200_key_t* d_keys, lb200_distance_t* d_distances, uint32_t* d_counts,
                                                   void* cuda_stream, lb200_error_t* error);
+/* Host-only check of a bootstrap collective (no device needed): every rank sends a rank-stamped blob through `allgather` the
+ * way group creation does and verifies what comes back.  Returns 0 when the callback behaves, a non-zero code otherwise. */
+LB200_EXPORT int lb200_group_selftest_exchange(int rank, int world, lb200_allgather_fn allgather, void* allgather_ctx);
 /* local_rank: 0 for a multi-process group; 0..n_devices-1 for a single-process one.  Synchronises that device. */
 LB200_EXPORT void lb200_group_last_stats(lb200_group_t, int local_rank, lb200_group_stats_t* stats, lb200_error_t* error);
 

@@ -140,6 +140,7 @@ SIGNATURES = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, ERRP]),
     "lb200_group_search_batch_device": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, ERRP]),
+    "lb200_group_selftest_exchange": (C.c_int, [C.c_int, C.c_int, ALLGATHER_FN, C.c_void_p]),
     "lb200_group_last_stats": (None, [C.c_void_p, C.c_int, C.POINTER(GroupStats), ERRP]),
     "lb200_device_count": (C.c_int, []),
     "lb200_version": (C.c_char_p, []),
@@ -323,13 +324,22 @@ class Group:
         _check(err)
         return cls(h, len(devices))
 
-    @classmethod
-    def ranked(cls, rank, world, allgather):
+    @staticmethod
+    def _callback(world, allgather):
         def _ag(ctx, send, recv, nbytes):
             out = allgather(C.string_at(send, nbytes))
             assert len(out) == nbytes * world, (len(out), nbytes, world)
             C.memmove(recv, out, len(out))
-        cb = ALLGATHER_FN(_ag)
+        return ALLGATHER_FN(_ag)
+
+    @staticmethod
+    def selftest_exchange(rank, world, allgather):
+        """Host-only: drives `allgather` through the C ABI exactly as group creation does; 0 = fine."""
+        return lib().lb200_group_selftest_exchange(rank, world, Group._callback(world, allgather), None)
+
+    @classmethod
+    def ranked(cls, rank, world, allgather):
+        cb = cls._callback(world, allgather)
         err = C.c_char_p()
         h = lib().lb200_group_create(rank, world, cb, None, C.byref(err))
         _check(err)

@@ -684,6 +684,22 @@ LB200_EXPORT void lb200_group_search_batch_device(lb200_group_t h, void const* d
                             (cudaStream_t)cuda_stream);
     });
 }
+LB200_EXPORT int lb200_group_selftest_exchange(int rank, int world, lb200_allgather_fn allgather, void* ctx) {
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || !allgather)
+        return 1;
+    for (size_t bytes : {(size_t)4, (size_t)136, (size_t)1000}) { // the sizes group creation / distribution exchange
+        std::vector<uint8_t> mine(bytes), all(bytes * (size_t)world, 0xEE);
+        for (size_t i = 0; i < bytes; ++i)
+            mine[i] = (uint8_t)(rank * 31 + i * 7 + bytes);
+        allgather(ctx, mine.data(), all.data(), bytes);
+        for (int r = 0; r < world; ++r)
+            for (size_t i = 0; i < bytes; ++i)
+                if (all[(size_t)r * bytes + i] != (uint8_t)(r * 31 + i * 7 + bytes))
+                    return 2;
+    }
+    return 0;
+}
+
 LB200_EXPORT void lb200_group_last_stats(lb200_group_t h, int local_rank, lb200_group_stats_t* stats, lb200_error_t* error) {
     guarded(error, [&] {
         if (!stats)

@@ -20,10 +20,12 @@
 // all-gather of SURVEY 8e, fused into the search epilogue); a last-warp-out flag exchange makes kernel completion imply
 // that all peers' results have landed.  No NCCL, no host synchronisation on the hot path.
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -738,13 +740,17 @@ class GroupRank {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t last_nq = 0;
     std::vector<void*> opened; // IPC mappings to close
+    void* d_in = nullptr;      // root: staging of the raw input queries of the host-buffer entry point
+    size_t in_bytes = 0;
+    std::vector<uint32_t> h_counts;
+    uint32_t h_err = 0;
 
     ~GroupRank() {
         cudaSetDevice(device);
         for (void* p : opened)
             cudaIpcCloseMemHandle(p);
         cudaFree(d_rows), cudaFree(d_adj0), cudaFree(d_upper_ref), cudaFree(d_upper_adj), cudaFree(d_keys);
-        cudaFree(slab), cudaFree(d_vis), cudaFree(d_touched), cudaFree(d_counters);
+        cudaFree(slab), cudaFree(d_vis), cudaFree(d_touched), cudaFree(d_counters), cudaFree(d_in);
         if (ev0)
             cudaEventDestroy(ev0);
         if (ev1)
@@ -1149,6 +1155,9 @@ void group_search_host(Group& G, const void* queries, size_t nq, size_t stride, 
         throw CudaError("group: lb200_group_distribute has not been called");
     if (!nq || !k)
         return;
+    const bool trace = getenv("LB200_GROUP_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = trace ? now() : 0;
     const size_t nr = G.ranks.size();
     GroupRank* r0 = G.ranks[0];
     const uint32_t L = beam_width(*r0, k, ef);
@@ -1162,7 +1171,6 @@ void group_search_host(Group& G, const void* queries, size_t nq, size_t stride, 
         }
     }
     renew_flags(G, G.streams);
-    void* d_in = nullptr;
     for (size_t i = 0; i < nr; ++i) {
         GroupRank* r = G.ranks[i];
         LB_CUDA(cudaSetDevice(r->device));
@@ -1170,38 +1178,50 @@ void group_search_host(Group& G, const void* queries, size_t nq, size_t stride, 
         if (r->rank == G.root) {
             if (!queries)
                 throw CudaError("group: the root rank must pass the queries");
-            LB_CUDA(cudaMallocAsync(&d_in, nq * in_bytes, G.streams[i]));
-            LB_CUDA(cudaMemcpy2DAsync(d_in, in_bytes, queries, stride, in_bytes, nq, cudaMemcpyHostToDevice, G.streams[i]));
-            dq = d_in;
+            // staging for the raw input rows: kept across calls (a stream-ordered allocation per call costs a round trip to
+            // the driver's pool each time)
+            if (nq * in_bytes > r->in_bytes) {
+                if (r->d_in)
+                    LB_CUDA(cudaFree(r->d_in));
+                r->d_in = nullptr;
+                r->in_bytes = nq * in_bytes + nq * in_bytes / 4;
+                LB_CUDA(cudaMalloc(&r->d_in, r->in_bytes));
+            }
+            LB_CUDA(cudaMemcpy2DAsync(r->d_in, in_bytes, queries, stride, in_bytes, nq, cudaMemcpyHostToDevice, G.streams[i]));
+            dq = r->d_in;
         }
         r->launch(dq, nq, in_bytes, kind, k, L, W, G.root, nullptr, nullptr, nullptr, G.streams[i]);
-        if (r->rank == G.root)
-            LB_CUDA(cudaFreeAsync(d_in, G.streams[i]));
     }
-    // results: from the first rank of this process (every rank holds all of them)
+    const double t1 = trace ? now() : 0;
+    // results: from the first rank of this process (every rank holds all of them); the error word rides along
     LB_CUDA(cudaSetDevice(r0->device));
     cudaStream_t s0 = G.streams[0];
     if (keys)
         LB_CUDA(cudaMemcpyAsync(keys, r0->slab + r0->lay.res_keys, nq * k * 8, cudaMemcpyDeviceToHost, s0));
     if (dists)
         LB_CUDA(cudaMemcpyAsync(dists, r0->slab + r0->lay.res_dists, nq * k * 4, cudaMemcpyDeviceToHost, s0));
-    std::vector<uint32_t> c32;
     if (counts) {
-        c32.resize(nq);
-        LB_CUDA(cudaMemcpyAsync(c32.data(), r0->slab + r0->lay.res_counts, nq * 4, cudaMemcpyDeviceToHost, s0));
+        r0->h_counts.resize(nq);
+        LB_CUDA(cudaMemcpyAsync(r0->h_counts.data(), r0->slab + r0->lay.res_counts, nq * 4, cudaMemcpyDeviceToHost, s0));
+    }
+    for (size_t i = 0; i < nr; ++i) {
+        GroupRank* r = G.ranks[i];
+        LB_CUDA(cudaSetDevice(r->device));
+        LB_CUDA(cudaMemcpyAsync(&r->h_err, r->slab + r->lay.err, 4, cudaMemcpyDeviceToHost, G.streams[i]));
     }
     for (size_t i = 0; i < nr; ++i) {
         LB_CUDA(cudaSetDevice(G.ranks[i]->device));
         LB_CUDA(cudaStreamSynchronize(G.streams[i]));
     }
-    for (size_t i = 0; i < nr; ++i) {
-        LB_CUDA(cudaSetDevice(G.ranks[i]->device));
-        G.ranks[i]->check_error();
-    }
+    const double t2 = trace ? now() : 0;
+    for (size_t i = 0; i < nr; ++i)
+        if (G.ranks[i]->h_err)
+            throw CudaError("group: a rank timed out waiting for a peer (rank " + std::to_string(G.ranks[i]->h_err - 1) + " gave up first)");
     if (counts)
         for (size_t i = 0; i < nq; ++i)
-            counts[i] = c32[i];
-    LB_CUDA(cudaSetDevice(r0->device));
+            counts[i] = r0->h_counts[i];
+    if (trace)
+        fprintf(stderr, "lb200 group rank %d: issue %.3f ms, wait %.3f ms\n", r0->rank, t1 - t0, t2 - t1);
 }
 
 void group_stats(Group& G, int which, GroupStats& out) {

@@ -130,6 +130,45 @@ def test_sharded_search_two_ranks_gloo(tmp_path):
         assert p.returncode == 0, o
 
 
+GROUP_WORKER = '''
+import os, sys
+sys.path.insert(0, {root!r})
+import torch.distributed as dist
+from lantern_b200 import api
+rank, world = int(os.environ["RANK"]), 2
+dist.init_process_group("gloo", rank=rank, world_size=world)
+def allgather(send):
+    outs = [None] * world
+    dist.all_gather_object(outs, send)
+    return b"".join(outs)
+# the bootstrap collective of a multi-process group, driven through the C ABI (no device needed for this part)
+assert api.Group.selftest_exchange(rank, world, allgather) == 0
+# ... and a broken collective is noticed
+assert api.Group.selftest_exchange(rank, world, lambda send: send * world) == (0 if False else 2)
+if api.device_count() == 0:  # the group itself has no CPU fallback
+    try:
+        api.Group.ranked(rank, world, allgather)
+        raise SystemExit("a group was created without a CUDA device")
+    except api.EngineError as e:
+        assert "CUDA device unavailable" in str(e), e
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_group_bootstrap_two_ranks_gloo(tmp_path):
+    """world_size=2, gloo, CPU: the all-gather callback a multi-process search group is bootstrapped with (lb200_group_create)
+    round-trips rank-stamped blobs through the C ABI; without a device the group refuses to exist."""
+    script = tmp_path / "group_worker.py"
+    script.write_text(GROUP_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29547", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+
+
 REF_HEADER_DIR = "/root/reference/lantern_hnsw/third_party/usearch/c"
 
 
