@@ -14,14 +14,17 @@ constexpr int kGroupMax = 8;
 struct GroupLaunch {
     uint32_t G, me, W, cap; // ranks, this rank, query slots (= resident warps) per GPU, ids per message (= M0)
     uint32_t ring_slots;    // rows a warp keeps in flight (its private bulk-copy ring)
+    uint32_t O, H;          // owner warps (one query each, slots 0..O) and helper warps (slots O..O+H) per GPU
     uint32_t nq, k, L;
     uint32_t flag_base; // message flags of this launch are flag_base + 1, +2, ...
     uint32_t epoch, root;
     unsigned long long timeout_ns;
     GraphView g; // g.vectors = this rank's row slice (row id - bounds[me]); adjacency, keys: whole graph, local copy
     uint32_t bounds[kGroupMax + 1];
-    unsigned long long* req[kGroupMax];  // [W][1 + cap] words {payload, flag}: header {count | DONE}, then ids
-    unsigned long long* resp[kGroupMax]; // [W][G][cap] words {distance bits, flag}
+    unsigned long long* req[kGroupMax];  // [G * O][1 + cap] words {payload, flag}: header {count | query << 9, or EXIT}, ids;
+                                         // mailbox src * O + oslot belongs to owner slot `oslot` of rank `src`
+    uint8_t* reqq[kGroupMax];            // [G * O][row_bytes] the query that owner slot is working on
+    unsigned long long* resp[kGroupMax]; // [O][G][cap] words {distance bits, flag}, per OWN owner slot
     uint64_t* res_keys[kGroupMax];       // [nq][k] final results, written by each query's owner into EVERY rank
     float* res_dists[kGroupMax];
     uint32_t* res_counts[kGroupMax];
@@ -30,8 +33,8 @@ struct GroupLaunch {
     uint32_t* err[kGroupMax];
     const uint8_t* queries; // the root's staging buffer (a peer address on the other ranks)
     uint32_t query_stride;
-    uint32_t* vis;     // owned slots: [W / G][words_per_slot]
-    uint32_t* touched; // [W / G][touched_cap]
+    uint32_t* vis;     // owner slots: [O][words_per_slot]
+    uint32_t* touched; // [O][touched_cap]
     size_t words_per_slot;
     uint32_t touched_cap;
     unsigned long long* counters; // [0] warps finished, [1] owner dist evals, [2] pops, [3] hops, [4] rounds, [5] local rows evaluated
