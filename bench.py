@@ -458,9 +458,28 @@ def run_ours(args, wl):
     # ---- ground truth for recall (untimed): brute force on this rank's shard, merged like the search results ----
     tk = torch.empty((nrec, k), dtype=torch.int64, device=dev)
     td = torch.empty((nrec, k), dtype=torch.float32, device=dev)
+    gt_info = None
     if not pq:
+        ge = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ge[0].record(stream)
         api.exact_search_device(X.data_ptr(), hi - lo, rowb, Q.data_ptr(), nrec, rowb, k, tk.data_ptr(), td.data_ptr(),
                                 wl["metric"], kind, dim, stream.cuda_stream)
+        ge[1].record(stream)
+        torch.cuda.synchronize()
+        gt_ms = ge[0].elapsed_time(ge[1])
+        tc = kind == "f32" and wl["metric"] in ("l2sq", "cos") and (hi - lo) >= 32768 and nrec >= 16 and not os.environ.get("LB200_EXACT")
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                tf32_peak = float(json.load(f)["bf16_tflops"]) / 2.0
+        except Exception:
+            tf32_peak = 1590.0 / 2.0
+        gt_info = {"rows": hi - lo, "queries": nrec, "k": k, "seconds": gt_ms / 1e3,
+                   "path": "tcgen05 3xTF32 filter + exact fp32 re-rank (csrc/exact_tc.cu)" if tc else "SIMT fp32 (csrc/exact.cu)"}
+        if tc:
+            tfl = 3 * 2.0 * (hi - lo) * nrec * dim / (gt_ms / 1e3) / 1e12
+            gt_info["roofline"] = {"bound": "tensor", "achieved": tfl, "unit": "TFLOP/s", "peak": tf32_peak,
+                                   "frac": tfl / tf32_peak, "flops": "3 tf32 MMAs per product (hi*hi + hi*lo + lo*hi), whole search incl. norms and re-rank",
+                                   "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (dense tf32 runs at half the bf16 rate)"}
         tk += lo + 1  # offsets -> global keys
     if world > 1:
         gk = torch.empty((world, nrec, k), dtype=torch.int64, device=dev)
@@ -625,7 +644,8 @@ def run_ours(args, wl):
                 "kernel_ms_per_step": kern_ms / args.steps,
                 "timing": "kernel_ms_per_step: CUDA events around the one kernel launch, in a SEPARATE pass over the same steps whose "
                           "stats read-back synchronises after every step (slightly slower than the back-to-back `ms_per_step`)", "algorithmic_bytes_per_step": alg_bytes / args.steps,
-                "dist_evals_per_query": n_dist / (args.steps * B), "pops_per_query": pops / (args.steps * B)}
+                "dist_evals_per_query": n_dist / (args.steps * B), "pops_per_query": pops / (args.steps * B),
+                "limbo_overflows_last_step": st.get("limbo_overflows", 0)}
 
     # ---- e2e through the reference-facing host call: pinned host buffers in/out, copies inside the timed region ----
     e2e = None
@@ -831,6 +851,7 @@ def run_ours(args, wl):
                        "x = z P + %.2f eps, z~N(0,I_%d), seeds %d/%d/%d" % (NOISE, LATENT, SEED_P, SEED_CORPUS, SEED_QUERY)},
             "recall_at_10": rec if k == 10 else None, "recall_at_k": rec, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "cpu_baseline_note": cpu_note, "parity": parity, "sharding": shard_info, "pq": pq_info,
+            "ground_truth": gt_info,
             "build": {"vectors_per_s": (hi - lo) / t_build, "seconds": t_build, "datagen_seconds": t_gen,
                       # SURVEY 8d build metric: sum of computed_distances(add) x bytes per stored vector / device time
                       "dist_evals_per_vector": build_work[0] / max(1, hi - lo), "device_seconds": build_work[2] / 1e3,

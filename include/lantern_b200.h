@@ -110,6 +110,8 @@ typedef struct lb200_search_stats_t {
     uint64_t upper_hops;         /* level>=1 neighbour lists scanned */
     uint64_t algorithmic_bytes;  /* computed_distances*row_bytes + (base_pops*(4+4*M0) + upper_hops*(4+4*M)) + queries*row_bytes */
     double kernel_ms;            /* device time of the search kernel alone (CUDA events on the launching stream) */
+    uint64_t limbo_overflows;    /* equal-distance candidates beyond the 64 the walker parks at the eviction boundary (only
+                                    possible with massive exact ties; each one may be an expansion the reference performs) */
 } lb200_search_stats_t;
 
 /* Work of the most recent lb200_build (or implicit build): the build metric of SURVEY.md 8d is

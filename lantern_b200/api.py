@@ -54,7 +54,8 @@ class IndexMetadata(C.Structure):  # == usearch_index_metadata_t (usearch.h:119-
 
 class SearchStats(C.Structure):
     _fields_ = [("queries", C.c_uint64), ("computed_distances", C.c_uint64), ("base_pops", C.c_uint64),
-                ("upper_hops", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("kernel_ms", C.c_double)]
+                ("upper_hops", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("kernel_ms", C.c_double),
+                ("limbo_overflows", C.c_uint64)]
 
 
 class BuildStats(C.Structure):

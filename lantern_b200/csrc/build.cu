@@ -314,7 +314,7 @@ static void build_pending_impl(Index& idx) {
     nseg.ensure(1);
 
     // work counters of this build (SURVEY 8d build metric: sum of computed_distances(add) x row bytes / time)
-    LB_CUDA(cudaMemsetAsync(idx.scratch_.counters, 0, 4 * sizeof(unsigned long long), stream));
+    LB_CUDA(cudaMemsetAsync(idx.scratch_.counters, 0, 8 * sizeof(unsigned long long), stream));
     LB_CUDA(cudaEventRecord(idx.ev0_, stream));
 
     size_t pos = 0;

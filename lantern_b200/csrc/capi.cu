@@ -322,6 +322,7 @@ LB200_EXPORT void lb200_last_search_stats(lb200_index_t h, lb200_search_stats_t*
         stats->upper_hops = s.upper_hops;
         stats->algorithmic_bytes = s.algorithmic_bytes;
         stats->kernel_ms = s.kernel_ms;
+        stats->limbo_overflows = s.limbo_overflows;
     });
 }
 

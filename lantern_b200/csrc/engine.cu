@@ -79,8 +79,8 @@ Index::Index(const IndexConfig& cfg, const float* codebook) : cfg_(cfg) {
         stored_bytes_ = vec_bytes_;
         row_bytes_ = round_up(vec_bytes_, 16);
     }
-    LB_CUDA(cudaMalloc(&scratch_.counters, 4 * sizeof(unsigned long long)));
-    LB_CUDA(cudaMemset(scratch_.counters, 0, 4 * sizeof(unsigned long long)));
+    LB_CUDA(cudaMalloc(&scratch_.counters, 8 * sizeof(unsigned long long)));
+    LB_CUDA(cudaMemset(scratch_.counters, 0, 8 * sizeof(unsigned long long)));
     LB_CUDA(cudaEventCreate(&ev0_));
     LB_CUDA(cudaEventCreate(&ev1_));
 }
@@ -364,7 +364,7 @@ void Index::search_device(const void* d_queries, size_t nq, size_t stride, int k
     }
     const uint32_t max_ctas = search_max_ctas(dist_mode_, cfg_.scalar_kind, gv, (uint32_t)L, cfg_.pq, expand);
     ensure_scratch(max_ctas);
-    LB_CUDA(cudaMemsetAsync(scratch_.counters, 0, 4 * sizeof(unsigned long long), stream));
+    LB_CUDA(cudaMemsetAsync(scratch_.counters, 0, 8 * sizeof(unsigned long long), stream));
 
     SearchLaunch p{};
     p.g = gv;
@@ -418,7 +418,7 @@ void Index::search_host(const void* queries, size_t nq, size_t stride, int kind,
 
 SearchStats Index::last_stats() {
     std::lock_guard<std::mutex> g(mu_);
-    unsigned long long c[4] = {0, 0, 0, 0};
+    unsigned long long c[8] = {0};
     LB_CUDA(cudaDeviceSynchronize());
     LB_CUDA(cudaMemcpy(c, scratch_.counters, sizeof(c), cudaMemcpyDeviceToHost));
     SearchStats s;
@@ -430,7 +430,7 @@ SearchStats Index::last_stats() {
         else
             (void)cudaGetLastError();
     }
-    s.computed_distances = c[1], s.base_pops = c[2], s.upper_hops = c[3];
+    s.computed_distances = c[1], s.base_pops = c[2], s.upper_hops = c[3], s.limbo_overflows = c[4];
     // B_alg = n_dist*bytes_per_stored_vector + n_pop*(4 + M_level*4) + query bytes
     s.algorithmic_bytes = s.computed_distances * (cfg_.pq ? stored_bytes_ : vec_bytes_) + s.base_pops * (4 + 4 * cfg_.M0) +
                           s.upper_hops * (4 + 4 * cfg_.M) + s.queries * vec_bytes_;

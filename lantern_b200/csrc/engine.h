@@ -34,7 +34,7 @@ struct IndexConfig {
 };
 
 struct SearchStats {
-    uint64_t queries = 0, computed_distances = 0, base_pops = 0, upper_hops = 0, algorithmic_bytes = 0;
+    uint64_t queries = 0, computed_distances = 0, base_pops = 0, upper_hops = 0, algorithmic_bytes = 0, limbo_overflows = 0;
     double kernel_ms = 0; // device time of the search kernel alone (CUDA events on the launching stream)
 };
 
@@ -63,7 +63,7 @@ struct GraphView {
 struct SearchScratch {
     uint32_t* visited;     // [ctas][words_per_cta]
     uint32_t* touched;     // [ctas][touched_cap]
-    unsigned long long* counters; // [0]=next query, [1]=dist evals, [2]=base pops, [3]=upper hops
+    unsigned long long* counters; // [0]=next query, [1]=dist evals, [2]=base pops, [3]=upper hops, [4]=limbo overflows (8 slots)
     size_t words_per_cta;
     uint32_t touched_cap;
     uint32_t ctas;

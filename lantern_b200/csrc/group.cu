@@ -540,11 +540,15 @@ template <int DM, int SK, int NQ> struct GroupWarp {
                             radius = td[size - 1];
                             if (limbo_n && radius < limbo_d)
                                 limbo_n = 0;
-                            if (ev_i != kNoNeighbor && !(ev_i & kExpandedBit) && ev_d == radius && limbo_n < kLimboCap) {
-                                if (lane == 0)
-                                    limbo()[limbo_n] = ev_i;
-                                limbo_n++, limbo_d = radius;
-                                __syncwarp();
+                            if (ev_i != kNoNeighbor && !(ev_i & kExpandedBit) && ev_d == radius) {
+                                if (limbo_n < kLimboCap) {
+                                    if (lane == 0)
+                                        limbo()[limbo_n] = ev_i;
+                                    limbo_n++, limbo_d = radius;
+                                    __syncwarp();
+                                } else if (lane == 0) {
+                                    atomicAdd(&p.counters[7], 1ull); // rare by construction
+                                }
                             }
                         }
                     }
@@ -714,6 +718,14 @@ __global__ void group_copy_results_kernel(const uint64_t* __restrict__ rk, const
 // =====================================================================================================================
 // host side
 // =====================================================================================================================
+
+// every spin in the kernel gives up after this long (LB200_GROUP_TIMEOUT_S, default 8 s; raise it under compute-sanitizer)
+static unsigned long long group_timeout_ns() {
+    double sec = 8.0;
+    if (const char* e = getenv("LB200_GROUP_TIMEOUT_S"))
+        sec = atof(e) > 0 ? atof(e) : sec;
+    return (unsigned long long)(sec * 1e9);
+}
 
 struct DeviceGuard { // the group switches devices; the caller's current device is put back when an entry point returns
     int dev = 0;
@@ -1002,7 +1014,7 @@ class GroupRank {
         p.nq = (uint32_t)nq, p.k = (uint32_t)k, p.L = L;
         p.flag_base = (epoch & 0xFFFu) << 20;
         p.epoch = epoch, p.root = (uint32_t)root;
-        p.timeout_ns = 8ull * 1000ull * 1000ull * 1000ull;
+        p.timeout_ns = group_timeout_ns();
         p.g.vectors = d_rows, p.g.adj0 = d_adj0, p.g.upper_ref = d_upper_ref, p.g.upper_adj = d_upper_adj, p.g.keys = d_keys;
         p.g.n = (uint32_t)n, p.g.row_bytes = (uint32_t)row_bytes, p.g.M = (uint32_t)cfg.M, p.g.M0 = (uint32_t)cfg.M0;
         p.g.entry = entry, p.g.max_level = max_level, p.g.flags = flags, p.g.dims = (uint32_t)cfg.dims;
@@ -1436,6 +1448,7 @@ void launch_warp_search(Index& idx, const uint8_t* qbuf, size_t qrow, size_t nq,
     });
     // work counters where Index::last_stats() reads them: [1] distance evaluations, [2] base pops, [3] upper hops
     LB_CUDA(cudaMemcpyAsync(idx.scratch_.counters + 1, p.counters + 1, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
+    LB_CUDA(cudaMemcpyAsync(idx.scratch_.counters + 4, p.counters + 7, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
 }
 
 void group_free(Group* G) {

@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(kWalkThreads) hnsw_search_kernel(const __grid_
         atomicAdd(&p.s.counters[1], (unsigned long long)w.st_dist);
         atomicAdd(&p.s.counters[2], (unsigned long long)w.st_pops);
         atomicAdd(&p.s.counters[3], (unsigned long long)w.st_hops);
+        if (w.st_limbo_drop)
+            atomicAdd(&p.s.counters[4], (unsigned long long)w.st_limbo_drop);
     }
 }
 

@@ -200,6 +200,7 @@ struct WalkBase {
     size_t words_per_cta;
     int warp, lane;
     uint32_t st_dist, st_pops, st_hops; // per-launch work counters; thread 0's copy is the one that is reported
+    uint32_t st_limbo_drop;             // equal-distance candidates that did not fit in limbo (the walk then expands fewer nodes)
 
     __device__ __forceinline__ explicit WalkBase(const GraphView& gv) : g(gv) {}
     __device__ __forceinline__ void init_base(uint8_t* smem_raw, const WalkLayout& lay, const SearchScratch& s) {
@@ -213,6 +214,7 @@ struct WalkBase {
         sm.ctrl = reinterpret_cast<WalkCtrl*>(smem_raw + lay.ctrl);
         warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         st_dist = st_pops = st_hops = 0;
+        st_limbo_drop = 0;
         vis = s.visited + (size_t)blockIdx.x * s.words_per_cta;
         touched = s.touched + (size_t)blockIdx.x * s.touched_cap;
         touched_cap = s.touched_cap;
@@ -527,6 +529,7 @@ template <class E> struct WalkerT : E {
     using E::st_dist;
     using E::st_hops;
     using E::st_pops;
+    using E::st_limbo_drop;
     using E::touched;
     using E::touched_cap;
     using E::vis;
@@ -703,11 +706,15 @@ template <class E> struct WalkerT : E {
                             radius = top.radius(lane);
                             if (limbo_n && radius < limbo_d)
                                 limbo_n = 0; // the radius shrank below the waiting ties: they can never be expanded
-                            if (ev_i != kNoNeighbor && !(ev_i & kExpandedBit) && ev_d == radius && limbo_n < kLimboCap) {
-                                if (lane == 0)
-                                    sm.limbo[limbo_n] = ev_i;
-                                limbo_n++, limbo_d = radius;
-                                __syncwarp();
+                            if (ev_i != kNoNeighbor && !(ev_i & kExpandedBit) && ev_d == radius) {
+                                if (limbo_n < kLimboCap) {
+                                    if (lane == 0)
+                                        sm.limbo[limbo_n] = ev_i;
+                                    limbo_n++, limbo_d = radius;
+                                    __syncwarp();
+                                } else {
+                                    this->st_limbo_drop += 1; // counted and reported (lb200_search_stats_t::limbo_overflows)
+                                }
                             }
                         }
                     }

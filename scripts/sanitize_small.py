@@ -37,4 +37,26 @@ g.search_batch(Q, k)
 g.close()
 api.exact_search(X, Q, k, "l2sq")
 api.exact_search(X, Q, k, "cos")
+# tensor-core exhaustive search (tcgen05 filter + re-rank), forced on this small problem
+os.environ["LB200_EXACT"] = "tc"
+kt, dt = api.exact_search(X, Q, k, "l2sq")
+os.environ["LB200_EXACT"] = "simt"
+ks, ds = api.exact_search(X, Q, k, "l2sq")
+os.environ.pop("LB200_EXACT")
+assert np.array_equal(kt, ks) and np.array_equal(dt.view(np.uint32), ds.view(np.uint32))
+# the warp-per-query kernel alone and as a two-rank group on one device (owner + helper pool, mailboxes, fused all-gather)
+g = api.Index(d, "cos", "f32", M=8, efc=32, ef=24)
+g.reserve(n)
+g.add_batch(np.arange(1, n + 1, dtype=np.uint64), X)
+g.build()
+k1, d1, _ = g.search_batch(Q, k)
+g.set_option("search_kernel", 2)
+k2, d2, _ = g.search_batch(Q, k)
+assert np.array_equal(k1, k2) and np.array_equal(d1.view(np.uint32), d2.view(np.uint32))
+grp = api.Group.local([0, 0])
+grp.distribute(g, root=0, max_batch=64)
+k3, d3, _ = grp.search_batch(Q, k)
+assert np.array_equal(k1, k3) and np.array_equal(d1.view(np.uint32), d3.view(np.uint32))
+grp.close()
+g.close()
 print("sanitize_small: done, %d kernel launches" % api.kernel_launches())

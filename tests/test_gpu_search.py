@@ -87,6 +87,7 @@ def test_hamming_bits(eng, port):
     ek, ed, _, etot = p.search_batch(Q, 10)
     assert np.array_equal(gk, ek) and np.array_equal(gd, ed)
     assert st["computed_distances"] == etot["computed_distances"]
+    assert st["limbo_overflows"] == 0  # the 64-entry tie buffer never overflowed: no expansion of the reference was skipped
 
 
 def test_k_larger_than_ef_and_small_index(eng, port):
