@@ -208,11 +208,23 @@ template <int DM, int SK, int NQ> struct GroupWarp {
         const uint32_t R = p.ring_slots;
         const uint32_t* ids = cand_id();
         const uint8_t* lj = loc();
+        // The ring keeps R rows in flight; the rows behind them are already on their way to L2 (one prefetch per 128-byte line,
+        // kPrefetchRows rows ahead), so a slot's refill is an L2 hit instead of a DRAM round trip.  With G GPUs a warp's share of
+        // an expansion is a handful of rows: all of them are requested from DRAM at once.
+        constexpr uint32_t kPrefetchRows = 8;
+        const uint32_t pf_off = (uint32_t)lane * 128u;
+        const bool pf_lane = pf_off < p.g.row_bytes;
+        const uint8_t* base = p.g.vectors - (size_t)p.bounds[p.me] * p.g.row_bytes;
+        for (uint32_t t = R; t < min(n, R + kPrefetchRows); ++t)
+            if (pf_lane)
+                prefetch_l2(base + (size_t)ids[OWNER ? lj[t] : t] * p.g.row_bytes + pf_off);
         if ((uint32_t)lane < min(n, R))
             issue_row(lane, ids[OWNER ? lj[lane] : lane]);
         uint32_t s = 0;
 #pragma unroll 1
         for (uint32_t t = 0; t < n; ++t) {
+            if (t + R + kPrefetchRows < n && pf_lane)
+                prefetch_l2(base + (size_t)ids[OWNER ? lj[t + R + kPrefetchRows] : t + R + kPrefetchRows] * p.g.row_bytes + pf_off);
             mbar_wait(bars() + s, (phase_bits >> s) & 1u);
             phase_bits ^= 1u << s;
             const uint4* row = reinterpret_cast<const uint4*>(ring() + (size_t)s * p.g.row_bytes);

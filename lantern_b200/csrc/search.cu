@@ -17,6 +17,7 @@
 // finally replays the reference's sequential insertions.  No row is read twice; besides rows the only HBM
 // traffic is one adjacency line per expansion and the bitmap words.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -75,23 +76,35 @@ __global__ void __launch_bounds__(kWalkThreads) hnsw_search_kernel(const __grid_
     }
 }
 
-template <class W> void launch_one(const SearchLaunch& p, uint32_t R, size_t smem, uint32_t grid, cudaStream_t stream) {
+template <class W> void launch_one(const SearchLaunch& p, uint32_t R, size_t smem, uint32_t grid, int threads, cudaStream_t stream) {
     auto kern = hnsw_search_kernel<W>;
     LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kWalkThreads, smem, stream>>>(p, R);
+    kern<<<grid, threads, smem, stream>>>(p, R);
     LB_CUDA(cudaGetLastError());
     count_launch();
 }
 
-template <class W> int occupancy_one(size_t smem) {
+template <class W> int occupancy_one(size_t smem, int threads) {
     auto kern = hnsw_search_kernel<W>;
     LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = 0;
-    LB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, kWalkThreads, smem));
+    LB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, threads, smem));
     return blocks;
 }
 
 } // namespace
+
+// Warps per query.  Wide rows: 4 (four warps stream a candidate list's rows in parallel).  Narrow rows (<= 1 KB: binary
+// vectors, short f16 / i8 rows): 2 -- the per-expansion serial chain of warp 0 (adjacency line, bitmap, insertions) is what
+// bounds them (ncu r02: `barrier` is the top stall, issue slots 52 % busy), so twice as many queries per SM with half the
+// waiting warps each is the better use of the SM.  LB200_SEARCH_WARPS overrides (experiments).
+static int search_threads(const GraphView& g, bool pq) {
+    int warps = (!pq && g.row_bytes <= 1024) ? 2 : 4;
+    if (const char* e = getenv("LB200_SEARCH_WARPS"))
+        if (!pq && (atoi(e) == 2 || atoi(e) == 4))
+            warps = atoi(e);
+    return warps * 32;
+}
 
 static size_t search_smem(const GraphView& g, bool pq, uint32_t R, uint32_t L, uint32_t expand) {
     return pq ? walk_layout_pq(g.num_subvectors, g.pq_lut_width, pq_value_floats(g), L, g.M0 * expand).total
@@ -105,7 +118,8 @@ uint32_t search_max_ctas(int dist_mode, int scalar_kind, const GraphView& g, uin
         throw CudaError("search: vectors wider than 8192 bytes are not supported");
     const size_t smem = search_smem(g, pq, R, L, expand);
     int occ = 0;
-    dispatch_walker(pq, dist_mode, scalar_kind, nq, [&](auto tag) { occ = occupancy_one<typename decltype(tag)::type>(smem); });
+    const int threads = search_threads(g, pq);
+    dispatch_walker(pq, dist_mode, scalar_kind, nq, [&](auto tag) { occ = occupancy_one<typename decltype(tag)::type>(smem, threads); });
     if (occ < 1)
         throw CudaError("search: kernel does not fit on an SM (ef/k or the pq table too large for shared memory)");
     return (uint32_t)occ * (uint32_t)device_sm_count();
@@ -116,8 +130,9 @@ void launch_search(int dist_mode, int scalar_kind, bool pq, const SearchLaunch& 
     const int nq = pq ? 1 : pick_nq(p.g.row_bytes);
     const size_t smem = search_smem(p.g, pq, R, p.L, p.expand);
     const uint32_t grid = p.s.ctas < p.nq ? p.s.ctas : p.nq;
+    const int threads = search_threads(p.g, pq);
     dispatch_walker(pq, dist_mode, scalar_kind, nq,
-                    [&](auto tag) { launch_one<typename decltype(tag)::type>(p, R, smem, grid, stream); });
+                    [&](auto tag) { launch_one<typename decltype(tag)::type>(p, R, smem, grid, threads, stream); });
 }
 
 } // namespace lb200

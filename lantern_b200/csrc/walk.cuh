@@ -230,13 +230,14 @@ template <int DM, int SK, int NQ> struct RowEval : WalkBase {
     uint4 qreg[NQ];
     float a2;
     uint32_t phase_bits;
-    uint32_t nchunks, R, SPW;
+    uint32_t nchunks, R, SPW, NW;
 
     __device__ __forceinline__ explicit RowEval(const GraphView& gv) : WalkBase(gv) {}
     __device__ __forceinline__ void init(uint8_t* smem_raw, const WalkLayout& lay, uint32_t ring_slots, const SearchScratch& s) {
         init_base(smem_raw, lay, s);
         nchunks = g.row_bytes / 16;
-        R = ring_slots, SPW = ring_slots / kWalkWarps;
+        NW = blockDim.x >> 5; // 4 warps per query, or 2 for narrow rows (search.cu): uniform across the CTA
+        R = ring_slots, SPW = ring_slots / NW;
         phase_bits = 0;
         a2 = 0.f;
         if (threadIdx.x == 0) {
@@ -286,21 +287,21 @@ template <int DM, int SK, int NQ> struct RowEval : WalkBase {
 
     // distances value -> cand_id[0..n) into cand_d[0..n).  Callers bracket it with __syncthreads().
     __device__ __forceinline__ void eval(uint32_t n) {
-        const uint32_t T = n > (uint32_t)warp ? (n - warp + kWalkWarps - 1) / kWalkWarps : 0;
+        const uint32_t T = n > (uint32_t)warp ? (n - warp + NW - 1) / NW : 0;
         if ((uint32_t)lane < min(T, SPW))
-            issue(warp + kWalkWarps * lane, sm.cand_id[warp + kWalkWarps * lane]);
+            issue(warp + NW * lane, sm.cand_id[warp + NW * lane]);
         uint32_t si = 0;
         for (uint32_t t = 0; t < T; ++t) {
-            const uint32_t slot = warp + kWalkWarps * si;
+            const uint32_t slot = warp + NW * si;
             mbar_wait(&sm.full[slot], (phase_bits >> si) & 1u);
             phase_bits ^= 1u << si;
             const float d = row_distance(reinterpret_cast<const uint4*>(sm.ring + (size_t)slot * g.row_bytes));
             if (lane == 0)
-                sm.cand_d[warp + kWalkWarps * t] = d;
+                sm.cand_d[warp + NW * t] = d;
             __syncwarp();
             if (t + SPW < T && lane == 0) {
                 fence_proxy_async(); // our generic-proxy reads of the slot precede the async refill
-                issue(slot, sm.cand_id[warp + kWalkWarps * (t + SPW)]);
+                issue(slot, sm.cand_id[warp + NW * (t + SPW)]);
             }
             si = (si + 1 == SPW) ? 0 : si + 1;
         }
@@ -730,10 +731,10 @@ template <class E> struct WalkerT : E {
         { // un-visit only the words this walk touched
             const uint32_t nt = sm.ctrl->ntouched;
             if (nt <= touched_cap) {
-                for (uint32_t i = threadIdx.x; i < nt; i += kWalkThreads)
+                for (uint32_t i = threadIdx.x; i < nt; i += blockDim.x)
                     vis[touched[i]] = 0u;
             } else {
-                for (size_t i = threadIdx.x; i < words_per_cta; i += kWalkThreads)
+                for (size_t i = threadIdx.x; i < words_per_cta; i += blockDim.x)
                     vis[i] = 0u;
             }
         }
@@ -756,7 +757,7 @@ template <class E> struct WalkerT : E {
             const uint32_t c_id = sm.top_i[consumed] & kIdMask;
             const float c_d = sm.top_d[consumed];
             load_node(c_id);
-            for (uint32_t j = threadIdx.x; j < submitted; j += kWalkThreads)
+            for (uint32_t j = threadIdx.x; j < submitted; j += blockDim.x)
                 sm.cand_id[j] = sm.top_i[j] & kIdMask;
             __syncthreads();
             eval(submitted);
