@@ -480,29 +480,71 @@ template <int DM, int SK, int NQ> struct GroupWarp {
                 if (c == kNoNeighbor)
                     break; // the beam is exhausted: index.hpp:3445 / queue empty
                 const uint32_t* list = p.g.adj0 + (size_t)c * M0;
-                for (uint32_t off = 0; off < M0; off += 32) {
-                    const uint32_t id = (off + lane < M0) ? __ldg(list + off + lane) : kNoNeighbor;
-                    const bool valid = id != kNoNeighbor;
-                    if (!__any_sync(0xffffffffu, valid))
-                        break;
-                    // duplicate ids inside one list are legal in reference graphs (refine_ padding, index.hpp:3554-3558)
-                    const uint32_t peers = __match_any_sync(0xffffffffu, id);
-                    const bool first = valid && ((uint32_t)(__ffs(peers) - 1) == (uint32_t)lane);
-                    bool fresh = false;
-                    if (first) {
-                        const uint32_t bit = 1u << (id & 31);
-                        fresh = !(atomicOr(&vis[id >> 5], bit) & bit);
+                if (M0 == 64) {
+                    // both halves of a 64-wide list at once: the two bitmap atomics of a lane are in flight together (one L2
+                    // atomic round trip per expansion instead of two).  Duplicates are legal in reference graphs (refine_
+                    // padding, index.hpp:3554-3558): only the FIRST occurrence in stored order may count as unseen, so the
+                    // second half is also checked against the first (through the candidate array, free at this point).
+                    const uint32_t id0 = __ldg(list + lane), id1 = __ldg(list + 32 + lane);
+                    const bool v0 = id0 != kNoNeighbor, v1 = id1 != kNoNeighbor;
+                    cand_id()[lane] = id0;
+                    __syncwarp();
+                    const uint32_t p0 = __match_any_sync(0xffffffffu, id0), p1 = __match_any_sync(0xffffffffu, id1);
+                    bool first0 = v0 && ((uint32_t)(__ffs(p0) - 1) == (uint32_t)lane);
+                    bool first1 = v1 && ((uint32_t)(__ffs(p1) - 1) == (uint32_t)lane);
+                    if (first1)
+                        for (int t = 0; t < 32; ++t)
+                            first1 &= cand_id()[t] != id1;
+                    __syncwarp();
+                    bool fresh0 = false, fresh1 = false;
+                    uint32_t old0 = 0, old1 = 0;
+                    const uint32_t bit0 = 1u << (id0 & 31), bit1 = 1u << (id1 & 31);
+                    if (first0)
+                        old0 = atomicOr(&vis[id0 >> 5], bit0);
+                    if (first1)
+                        old1 = atomicOr(&vis[id1 >> 5], bit1);
+                    fresh0 = first0 && !(old0 & bit0), fresh1 = first1 && !(old1 & bit1);
+                    const uint32_t m0 = __ballot_sync(0xffffffffu, fresh0), m1 = __ballot_sync(0xffffffffu, fresh1);
+                    const uint32_t lt = (1u << lane) - 1u, n0 = __popc(m0);
+                    if (fresh0) {
+                        const uint32_t r = __popc(m0 & lt);
+                        cand_id()[r] = id0;
+                        if (ntouched + r < p.touched_cap)
+                            touched[ntouched + r] = id0 >> 5;
                     }
-                    const uint32_t m = __ballot_sync(0xffffffffu, fresh);
-                    const uint32_t rank = __popc(m & ((1u << lane) - 1u));
-                    if (fresh) {
-                        cand_id()[n + rank] = id;
-                        if (ntouched + rank < p.touched_cap)
-                            touched[ntouched + rank] = id >> 5;
+                    __syncwarp(); // (the compaction above overwrites entries another lane compared against: all compares are done)
+                    if (fresh1) {
+                        const uint32_t r = n0 + __popc(m1 & lt);
+                        cand_id()[r] = id1;
+                        if (ntouched + r < p.touched_cap)
+                            touched[ntouched + r] = id1 >> 5;
                     }
-                    n += __popc(m);
-                    ntouched += __popc(m);
-                }
+                    n = n0 + __popc(m1);
+                    ntouched += n;
+                } else
+                    for (uint32_t off = 0; off < M0; off += 32) {
+                        const uint32_t id = (off + lane < M0) ? __ldg(list + off + lane) : kNoNeighbor;
+                        const bool valid = id != kNoNeighbor;
+                        if (!__any_sync(0xffffffffu, valid))
+                            break;
+                        // duplicate ids inside one list are legal in reference graphs (refine_ padding, index.hpp:3554-3558)
+                        const uint32_t peers = __match_any_sync(0xffffffffu, id);
+                        const bool first = valid && ((uint32_t)(__ffs(peers) - 1) == (uint32_t)lane);
+                        bool fresh = false;
+                        if (first) {
+                            const uint32_t bit = 1u << (id & 31);
+                            fresh = !(atomicOr(&vis[id >> 5], bit) & bit);
+                        }
+                        const uint32_t m = __ballot_sync(0xffffffffu, fresh);
+                        const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+                        if (fresh) {
+                            cand_id()[n + rank] = id;
+                            if (ntouched + rank < p.touched_cap)
+                                touched[ntouched + rank] = id >> 5;
+                        }
+                        n += __popc(m);
+                        ntouched += __popc(m);
+                    }
                 st_pops += 1;
             }
             __syncwarp();

@@ -65,6 +65,39 @@ def test_group_equals_one_gpu(eng, ranks, metric, quant, d):
     grp.close()
 
 
+@pytest.mark.parametrize("M", [32, 48])
+def test_group_wide_lists(eng, M):
+    """M = 32 (the metric's configuration: 64-wide base lists take the two-halves-at-once path, where a duplicate id may sit in
+    either half) and M = 48 (96-wide lists, the general path); duplicates are planted on purpose in a few lists."""
+    g, X, Q = _index(eng, "cos", "f32", 64, 5000, M=M, efc=96, ef=64)
+    # plant duplicates the way refine_'s stale padding produces them: rewrite the file, load it back
+    buf = g.save_buffer().copy()
+    n = 5000
+    off, planted = 136, 0
+    for i in range(n):
+        lvl = int(np.frombuffer(buf, np.int16, 1, off + 8)[0])
+        base = off + 10
+        cnt = int(np.frombuffer(buf, np.uint32, 1, base)[0])
+        if i % 7 == 0 and cnt >= 40:
+            ids = buf[base + 4: base + 4 + 6 * cnt].reshape(cnt, 6)
+            ids[cnt - 1] = ids[2]      # second half repeats an id of the first half
+            ids[5] = ids[4]            # and a duplicate inside the first half
+            planted += 1
+        off = base + 4 + 12 * M + lvl * (4 + 6 * M) + 64 * 4
+    assert planted > 50
+    g2 = eng.Index(64, "cos", "f32", M=M, efc=96, ef=64)
+    g2.load_buffer(buf)
+    k1, d1, c1 = g2.search_batch(Q, 10, 64)
+    st1 = g2.last_stats()
+    ndev = eng.device_count()
+    grp = eng.Group.local([r % ndev for r in range(2)])
+    grp.distribute(g2, root=0, max_batch=512)
+    kg, dg, cg = grp.search_batch(Q, 10, 64)
+    assert np.array_equal(kg, k1) and np.array_equal(dg.view(np.uint32), d1.view(np.uint32)) and np.array_equal(cg, c1)
+    assert sum(grp.last_stats(r)["owner_computed_distances"] for r in range(2)) == st1["computed_distances"]
+    grp.close()
+
+
 def test_group_wide_beam_small_batch_and_k(eng):
     """ef = 400, k = 100, fewer queries than ranks, and a batch that is not a multiple of the rank count."""
     g, X, Q = _index(eng, "l2sq", "f32", 48, 5000, M=8, efc=48, ef=64)
