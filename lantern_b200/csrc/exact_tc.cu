@@ -186,43 +186,47 @@ template <int DM> __global__ void __launch_bounds__(kTcThreads, 1) exact_tc_filt
             const size_t row0 = (size_t)(g + t * p.groups) * kTileN;
             for (uint32_t kb = 0; kb < KB; ++kb, ++it) {
                 const uint32_t s = it % kStages;
-                mbar_wait(&empty_bar[s], ((it / kStages) & 1u) ^ 1u);
                 uint8_t* st = smem + (size_t)s * kStageBytes;
-                // A: 128 query rows = 4 slabs of 32 rows, one per producer warp; lane = row within the slab
-                {
-                    const uint32_t r = pw * 32 + lane, q = q0 + r;
-                    const uint4* src = reinterpret_cast<const uint4*>(p.queries + (size_t)q * p.q_stride) + kb * 8;
-                    uint4 v[8];
+                // A: 128 query rows = 4 slabs of 32 rows, one per producer warp; B: 256 corpus rows = 8 slabs, two per warp;
+                // lane = row within the slab.  All 24 16-byte loads of the k-block are issued before the first conversion
+                // (one memory latency per k-block instead of three), and the thread's three 128-byte lines of the NEXT
+                // k-block are requested into L2 meanwhile.
+                const uint32_t ra = pw * 32 + lane, qa = q0 + ra;
+                const uint32_t rb0 = (pw * 2) * 32 + lane, rb1 = rb0 + 32;
+                const size_t row_b0 = row0 + rb0, row_b1 = row0 + rb1;
+                const uint4* sa = reinterpret_cast<const uint4*>(p.queries + (size_t)qa * p.q_stride) + kb * 8;
+                const uint4* sb0 = reinterpret_cast<const uint4*>(p.data + row_b0 * p.data_stride) + kb * 8;
+                const uint4* sb1 = reinterpret_cast<const uint4*>(p.data + row_b1 * p.data_stride) + kb * 8;
+                uint4 va[8], vb0[8], vb1[8];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        v[c] = (q < p.nq && kb * 8 + c < p.nchunks) ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
-                    uint8_t* dst = st + (r >> 3) * 1024 + (r & 7) * 16;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        uint4 hi, lo;
-                        split4(v[c], hi, lo);
-                        *reinterpret_cast<uint4*>(dst + c * 128) = hi;
-                        *reinterpret_cast<uint4*>(dst + kABytes + c * 128) = lo;
-                    }
+                for (int c = 0; c < 8; ++c) {
+                    const bool in_k = kb * 8 + c < p.nchunks;
+                    va[c] = (qa < p.nq && in_k) ? __ldg(sa + c) : make_uint4(0, 0, 0, 0);
+                    vb0[c] = (row_b0 < p.n && in_k) ? __ldg(sb0 + c) : make_uint4(0, 0, 0, 0);
+                    vb1[c] = (row_b1 < p.n && in_k) ? __ldg(sb1 + c) : make_uint4(0, 0, 0, 0);
                 }
-                // B: 256 corpus rows = 8 slabs, two per producer warp
-#pragma unroll 1
-                for (int sl = 0; sl < 2; ++sl) {
-                    const uint32_t r = (pw * 2 + sl) * 32 + lane;
-                    const size_t row = row0 + r;
-                    const uint4* src = reinterpret_cast<const uint4*>(p.data + row * p.data_stride) + kb * 8;
-                    uint4 v[8];
+                if ((kb + 1) * 8 < p.nchunks) {
+                    if (row_b0 < p.n)
+                        prefetch_l2(sb0 + 8);
+                    if (row_b1 < p.n)
+                        prefetch_l2(sb1 + 8);
+                }
+                mbar_wait(&empty_bar[s], ((it / kStages) & 1u) ^ 1u); // (the loads above are already in flight)
+                uint8_t* da = st + (ra >> 3) * 1024 + (ra & 7) * 16;
+                uint8_t* db0 = st + 2 * kABytes + (rb0 >> 3) * 1024 + (rb0 & 7) * 16;
+                uint8_t* db1 = st + 2 * kABytes + (rb1 >> 3) * 1024 + (rb1 & 7) * 16;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        v[c] = (row < p.n && kb * 8 + c < p.nchunks) ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
-                    uint8_t* dst = st + 2 * kABytes + (r >> 3) * 1024 + (r & 7) * 16;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        uint4 hi, lo;
-                        split4(v[c], hi, lo);
-                        *reinterpret_cast<uint4*>(dst + c * 128) = hi;
-                        *reinterpret_cast<uint4*>(dst + kBBytes + c * 128) = lo;
-                    }
+                for (int c = 0; c < 8; ++c) {
+                    uint4 hi, lo;
+                    split4(va[c], hi, lo);
+                    *reinterpret_cast<uint4*>(da + c * 128) = hi;
+                    *reinterpret_cast<uint4*>(da + kABytes + c * 128) = lo;
+                    split4(vb0[c], hi, lo);
+                    *reinterpret_cast<uint4*>(db0 + c * 128) = hi;
+                    *reinterpret_cast<uint4*>(db0 + kBBytes + c * 128) = lo;
+                    split4(vb1[c], hi, lo);
+                    *reinterpret_cast<uint4*>(db1 + c * 128) = hi;
+                    *reinterpret_cast<uint4*>(db1 + kBBytes + c * 128) = lo;
                 }
                 fence_proxy_async(); // generic-proxy stores above -> visible to the tensor core's async-proxy reads
                 __syncwarp();

@@ -773,9 +773,9 @@ __global__ void group_copy_results_kernel(const uint64_t* __restrict__ rk, const
 // host side
 // =====================================================================================================================
 
-// every spin in the kernel gives up after this long (LB200_GROUP_TIMEOUT_S, default 8 s; raise it under compute-sanitizer)
+// every spin in the kernel gives up after this long (LB200_GROUP_TIMEOUT_S, default 20 s; raise it under compute-sanitizer)
 static unsigned long long group_timeout_ns() {
-    double sec = 8.0;
+    double sec = 20.0;
     if (const char* e = getenv("LB200_GROUP_TIMEOUT_S"))
         sec = atof(e) > 0 ? atof(e) : sec;
     return (unsigned long long)(sec * 1e9);
@@ -1019,6 +1019,10 @@ class GroupRank {
         LB_CUDA(cudaMalloc(&d_touched, owned * (size_t)touched_cap * 4));
         LB_CUDA(cudaMalloc(&d_counters, 8 * sizeof(unsigned long long)));
         LB_CUDA(cudaMemset(d_counters, 0, 8 * sizeof(unsigned long long)));
+        // staging of raw input queries for the host-buffer entry point: allocated NOW -- a cudaMalloc between the launches of a
+        // search may wait for kernels already running on this device, and those kernels wait for the rank that is allocating
+        in_bytes = max_batch * std::max<size_t>(row_bytes, cfg.dims * 4);
+        LB_CUDA(cudaMalloc(&d_in, in_bytes));
         LB_CUDA(cudaEventCreate(&ev0));
         LB_CUDA(cudaEventCreate(&ev1));
         LB_CUDA(cudaDeviceSynchronize());
@@ -1313,22 +1317,20 @@ void group_search_host(Group& G, const void* queries, size_t nq, size_t stride, 
         }
     }
     renew_flags(G, G.streams);
-    for (size_t i = 0; i < nr; ++i) {
+    size_t first = 0; // the root goes first: its (possibly pageable, hence host-blocking) upload must not sit behind kernels that
+    for (size_t i = 0; i < nr; ++i) // already spin on the same device waiting for the root's queries
+        if (G.ranks[i]->rank == G.root)
+            first = i;
+    for (size_t step = 0; step < nr; ++step) {
+        const size_t i = (first + step) % nr;
         GroupRank* r = G.ranks[i];
         LB_CUDA(cudaSetDevice(r->device));
         const void* dq = nullptr;
         if (r->rank == G.root) {
             if (!queries)
                 throw CudaError("group: the root rank must pass the queries");
-            // staging for the raw input rows: kept across calls (a stream-ordered allocation per call costs a round trip to
-            // the driver's pool each time)
-            if (nq * in_bytes > r->in_bytes) {
-                if (r->d_in)
-                    LB_CUDA(cudaFree(r->d_in));
-                r->d_in = nullptr;
-                r->in_bytes = nq * in_bytes + nq * in_bytes / 4;
-                LB_CUDA(cudaMalloc(&r->d_in, r->in_bytes));
-            }
+            if (nq * in_bytes > r->in_bytes) // (sized for max_batch at distribution time; nothing may be allocated here)
+                throw CudaError("group: batch larger than the group was created for (max_batch)");
             LB_CUDA(cudaMemcpy2DAsync(r->d_in, in_bytes, queries, stride, in_bytes, nq, cudaMemcpyHostToDevice, G.streams[i]));
             dq = r->d_in;
         }

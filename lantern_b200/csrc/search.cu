@@ -94,12 +94,12 @@ template <class W> int occupancy_one(size_t smem, int threads) {
 
 } // namespace
 
-// Warps per query.  Wide rows: 4 (four warps stream a candidate list's rows in parallel).  Narrow rows (<= 1 KB: binary
-// vectors, short f16 / i8 rows): 2 -- the per-expansion serial chain of warp 0 (adjacency line, bitmap, insertions) is what
-// bounds them (ncu r02: `barrier` is the top stall, issue slots 52 % busy), so twice as many queries per SM with half the
-// waiting warps each is the better use of the SM.  LB200_SEARCH_WARPS overrides (experiments).
+// Warps per query: 4.  Two warps per query (twice the CTAs per SM, half the warps waiting at each barrier) was measured for
+// 768-byte rows in round 2 and changed nothing (2.48 vs 2.50 M q/s on cfg5t, profiles/r02_bench_cfg5t_w*.json): the narrow-row
+// bound is the per-expansion latency chain itself, not the idle warps.  LB200_SEARCH_WARPS = 2 keeps the experiment runnable.
 static int search_threads(const GraphView& g, bool pq) {
-    int warps = (!pq && g.row_bytes <= 1024) ? 2 : 4;
+    (void)g;
+    int warps = 4;
     if (const char* e = getenv("LB200_SEARCH_WARPS"))
         if (!pq && (atoi(e) == 2 || atoi(e) == 4))
             warps = atoi(e);
