@@ -7,7 +7,7 @@
 //   1. norms_kernel            |x|^2 of every row and query (fp32)
 //   2. exact_tc_filter_kernel  D = Q . X^T on tcgen05 in "3xTF32" (a = hi + lo with hi, lo representable in tf32;
 //                              q.x ~ qhi.xhi + qhi.xlo + qlo.xhi, fp32 accumulation in TMEM), fused epilogue: distance
-//                              from norms and dot product, per-query sorted candidate list of KP > k entries per row
+//                              from norms and dot product, per-query candidate list (a max-heap) of KP > k entries per row
 //                              group, plus the smallest lower bound of anything the list had to drop
 //   3. exact_tc_rerank_kernel  per query: candidates whose lower bound (approx - eps) does not exceed the k-th smallest
 //                              upper bound (approx + eps) are re-measured with the SIMT distance code of exact.cu
@@ -125,7 +125,7 @@ struct TcParams {
     uint32_t row_tiles;
     uint32_t KP;
     float eps_rel;
-    float* cand_d;    // [nq][groups][KP] ascending approx distances (+inf padded)
+    float* cand_d;    // [nq][groups][KP] approx distances of the kept rows, heap order (+inf padded)
     uint32_t* cand_i; // [nq][groups][KP]
     float* dropped_lb; // [nq][groups] smallest lower bound among entries the list could not keep (+inf if none)
 };
@@ -301,22 +301,38 @@ template <int DM> __global__ void __launch_bounds__(kTcThreads, 1) exact_tc_filt
                         if (row < p.n) {
                             const float xn = __ldg(p.xn + row);
                             const float d = approx_distance<DM>(__uint_as_float(r[j]), qn, xn);
-                            if (d < thr) { // sorted insert; the evicted tail (if any) is remembered through its lower bound
+                            if (d < thr) {
+                                // max-heap on the distance (root = the list's current worst, = thr once the list is full):
+                                // log2(KP) steps per accepted row.  A sorted array cost KP/2 shifts per insert, and every
+                                // insert of ANY lane stalls the whole warp (ncu: the shift loop was the kernel's hot spot).
                                 uint32_t pos;
-                                if (size == KP) {
-                                    const uint32_t lid = li[KP - 1];
-                                    dropped = fminf(dropped, ld[KP - 1] - approx_eps<DM>(p.eps_rel, qn, __ldg(p.xn + lid)));
-                                    pos = KP - 1;
-                                } else {
+                                if (size < KP) {
                                     pos = size++;
-                                }
-                                while (pos > 0 && ld[pos - 1] > d) {
-                                    ld[pos] = ld[pos - 1], li[pos] = li[pos - 1];
-                                    --pos;
+                                    while (pos > 0) {
+                                        const uint32_t par = (pos - 1) >> 1;
+                                        if (ld[par] >= d)
+                                            break;
+                                        ld[pos] = ld[par], li[pos] = li[par];
+                                        pos = par;
+                                    }
+                                } else { // replace the root; the evicted row is remembered through its lower bound
+                                    dropped = fminf(dropped, ld[0] - approx_eps<DM>(p.eps_rel, qn, __ldg(p.xn + li[0])));
+                                    pos = 0;
+                                    for (;;) {
+                                        uint32_t c = 2 * pos + 1;
+                                        if (c >= KP)
+                                            break;
+                                        if (c + 1 < KP && ld[c + 1] > ld[c])
+                                            ++c;
+                                        if (ld[c] <= d)
+                                            break;
+                                        ld[pos] = ld[c], li[pos] = li[c];
+                                        pos = c;
+                                    }
                                 }
                                 ld[pos] = d, li[pos] = (uint32_t)row;
                                 if (size == KP)
-                                    thr = ld[KP - 1];
+                                    thr = ld[0];
                             } else {
                                 dropped = fminf(dropped, d - approx_eps<DM>(p.eps_rel, qn, xn));
                             }
