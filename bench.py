@@ -990,7 +990,8 @@ def run_group(args, wl):
     step_device(args.warmup)
     st = grp.last_stats()
     mine = torch.tensor([st["local_rows_evaluated"], st["local_row_bytes"], st["owner_computed_distances"], st["owner_base_pops"],
-                         st["owner_upper_hops"], st["owner_rounds"], st["kernel_ms"] * 1e6], dtype=torch.float64, device=dev)
+                         st["owner_upper_hops"], st["owner_rounds"], st["kernel_ms"] * 1e6, st["owner_cycles_produce"],
+                         st["owner_cycles_local"], st["owner_cycles_wait"], st["owner_cycles_consume"]], dtype=torch.float64, device=dev)
     allst = torch.empty((world, mine.numel()), dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(allst, mine)
     allst = allst.cpu().numpy()
@@ -1033,8 +1034,12 @@ def run_group(args, wl):
         vec_bytes = rowb
         alg = float(allst[:, 2].sum() * vec_bytes + allst[:, 3].sum() * (4 + 8 * wl["M"]) + allst[:, 4].sum() * (4 + 4 * wl["M"]) + B * vec_bytes)
         kms = float(allst[:, 6].max() / 1e6)
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
         per_rank = [{"rank": r, "rows_evaluated_per_query": float(allst[r, 0] / B), "row_gb_per_step": float(allst[r, 1] / 1e9),
-                     "kernel_ms": float(allst[r, 6] / 1e6), "local_hbm_frac": float(allst[r, 1] / (allst[r, 6] / 1e9) / 1e9 / peak)}
+                     "kernel_ms": float(allst[r, 6] / 1e6), "local_hbm_frac": float(allst[r, 1] / (allst[r, 6] / 1e9) / 1e9 / peak),
+                     # where an owner warp's time goes, per expansion round (SM cycles / sampled SM clock)
+                     "owner_us_per_round": {name: float(allst[r, 7 + i] / max(allst[r, 5], 1.0) / mhz)
+                                            for i, name in enumerate(("produce_ids", "local_rows", "wait_for_peers", "insertions"))}}
                     for r in range(world)]
         roofline = {"bound": "hbm", "achieved": alg / (kms / 1e3) / 1e9, "peak": peak * world, "unit": "GB/s",
                     "frac": alg / (kms / 1e3) / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src + " x %d GPUs" % world,

@@ -284,6 +284,9 @@ typedef struct lb200_group_stats_t {
     uint64_t local_row_bytes;      /* local_rows_evaluated * bytes per stored vector */
     uint64_t rows_held;
     double kernel_ms; /* device time of this rank's search kernel (CUDA events on its stream) */
+    /* where the owner warps of this rank spent their SM cycles (summed over the warps): producing a round's ids (pop, adjacency
+     * line, visited bitmap), measuring their local rows, waiting for the other ranks' distances, consuming (ordered insertions) */
+    uint64_t owner_cycles_produce, owner_cycles_local, owner_cycles_wait, owner_cycles_consume;
 } lb200_group_stats_t;
 LB200_EXPORT lb200_group_t lb200_group_create(int rank, int world, lb200_allgather_fn allgather, void* allgather_ctx,
                                               lb200_error_t* error);

@@ -67,7 +67,8 @@ class GroupStats(C.Structure):
     _fields_ = [("rank", C.c_int), ("world", C.c_int), ("queries", C.c_uint64), ("owner_computed_distances", C.c_uint64),
                 ("owner_base_pops", C.c_uint64), ("owner_upper_hops", C.c_uint64), ("owner_rounds", C.c_uint64),
                 ("local_rows_evaluated", C.c_uint64), ("local_row_bytes", C.c_uint64), ("rows_held", C.c_uint64),
-                ("kernel_ms", C.c_double)]
+                ("kernel_ms", C.c_double), ("owner_cycles_produce", C.c_uint64), ("owner_cycles_local", C.c_uint64),
+                ("owner_cycles_wait", C.c_uint64), ("owner_cycles_consume", C.c_uint64)]
 
 
 ALLGATHER_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)

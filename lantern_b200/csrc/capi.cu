@@ -715,6 +715,8 @@ LB200_EXPORT void lb200_group_last_stats(lb200_group_t h, int local_rank, lb200_
         stats->local_rows_evaluated = s.local_rows_evaluated, stats->local_row_bytes = s.local_row_bytes;
         stats->rows_held = s.rows_held;
         stats->kernel_ms = s.kernel_ms;
+        stats->owner_cycles_produce = s.owner_cycles_produce, stats->owner_cycles_local = s.owner_cycles_local;
+        stats->owner_cycles_wait = s.owner_cycles_wait, stats->owner_cycles_consume = s.owner_cycles_consume;
     });
 }
 

@@ -10,15 +10,18 @@
 // GPU that owns the row.  Total row traffic is that of the 1-GPU search, split G ways; the results are those of the 1-GPU
 // search on the same graph, id for id (same decision sequence, same fp32 reduction order).
 //
-// Mapping to the machine.  Every GPU runs the same persistent kernel with W resident warps; warp `slot` serves query
-// slot, slot+W, ... on EVERY GPU at once: on GPU (slot mod G) it is the query's owner (top list, visited bitmap, the
-// reference's decisions), on the others a helper that keeps the query in shared memory and evaluates the rows it holds.
-// Per expansion the owner sends each helper the ids of the unseen neighbours that live there and receives their
-// distances; messages are 8-byte words {payload, flag} written straight into the peer's HBM over NVLink (peer-mapped
-// memory; NCCL's "LL" idea: the flag travels with the data, so no fence is needed and one NVLink write latency is the
-// whole cost) and polled locally.  The final top-k of a query is stored into every GPU's result buffer by its owner (the
-// all-gather of SURVEY 8e, fused into the search epilogue); a last-warp-out flag exchange makes kernel completion imply
-// that all peers' results have landed.  No NCCL, no host synchronisation on the hot path.
+// Mapping to the machine.  Every GPU runs the same persistent kernel of independent warps (no CTA-wide barrier anywhere).
+// The first O warps are OWNERS: each takes one of this GPU's queries (q mod G == rank) at a time, keeps the query in
+// registers, the top list in shared memory, the visited bitmap in HBM, and makes the reference's decisions.  The other H
+// warps are a HELPER POOL that measures local rows for remote owners: the (G-1)*O inbound mailboxes are dealt round-robin
+// to the helpers, one lane watching one mailbox.  Per expansion the owner sends each rank the ids of the unseen neighbours
+// that live there and receives their distances; messages are 8-byte words {payload, flag} written straight into the peer's
+// HBM over NVLink (peer-mapped memory; NCCL's "LL" idea: the flag travels with the data, so no fence is needed and one
+// NVLink write latency is the whole cost) and polled locally.  Rows are fetched through a per-warp bulk-copy ring
+// (cp.async.bulk + mbarrier) behind an L2 prefetch of the rows to come.  The final top-k of a query is stored into every
+// GPU's result buffer by its owner (the all-gather of SURVEY 8e, fused into the search epilogue); a last-warp-out flag
+// exchange makes kernel completion imply that all peers' results have landed.  No NCCL, no host synchronisation on the hot
+// path.  With G = 1 the same kernel is a one-warp-per-query single-GPU search (launch_warp_search).
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -121,6 +124,8 @@ template <int DM, int SK, int NQ> struct GroupWarp {
     bool dead, waited;
     unsigned long long t0;
     uint32_t st_dist, st_pops, st_hops, st_rounds, st_rows;
+    // owner: SM cycles spent producing a round's ids, measuring the local rows, waiting for the helpers, consuming
+    uint32_t cy_produce, cy_local, cy_wait, cy_consume; // (32 bits: 2 s of cycles per warp and launch)
 
     __device__ __forceinline__ explicit GroupWarp(const GroupLaunch& gp) : p(gp) {}
 
@@ -288,7 +293,10 @@ template <int DM, int SK, int NQ> struct GroupWarp {
             st_sys_u64(p.req[lane] + ((size_t)me * p.O + slot) * (1 + cap), pack_word(cnt | (cur_q << kMsgCountBits), flag));
         const uint32_t nloc = __shfl_sync(0xffffffffu, cnt, me);
         __syncwarp();
+        const uint32_t c0 = (uint32_t)clock64();
         eval_local<true>(nloc);
+        const uint32_t c1 = (uint32_t)clock64();
+        cy_local += c1 - c0;
         const unsigned long long* inbox = p.resp[me] + (size_t)slot * G * cap;
 #pragma unroll 1
         for (uint32_t base = 0; base < n; base += 32) {
@@ -300,6 +308,7 @@ template <int DM, int SK, int NQ> struct GroupWarp {
             }
         }
         dead = __any_sync(0xffffffffu, dead);
+        cy_wait += (uint32_t)clock64() - c1;
         st_rounds += 1;
         __syncwarp();
     }
@@ -437,6 +446,7 @@ template <int DM, int SK, int NQ> struct GroupWarp {
 #pragma unroll 1
         while (!dead) {
             // ---- produce the ids to measure ----
+            const uint32_t cp0 = (uint32_t)clock64();
             uint32_t n = 0;
             if (level < 0) {
                 if (lane == 0)
@@ -548,11 +558,14 @@ template <int DM, int SK, int NQ> struct GroupWarp {
                 st_pops += 1;
             }
             __syncwarp();
+            const uint32_t cp1 = (uint32_t)clock64();
             // ---- evaluate: every id on the GPU that holds its row ----
             if (n)
                 eval_round(n);
             if (dead)
                 break;
+            const uint32_t cp2 = (uint32_t)clock64();
+            cy_produce += cp1 - cp0; // classification + sends are counted with the evaluation
             st_dist += n;
             // ---- consume ----
             if (level < 0) {
@@ -609,6 +622,7 @@ template <int DM, int SK, int NQ> struct GroupWarp {
                 }
                 __syncwarp();
             }
+            cy_consume += (uint32_t)clock64() - cp2;
             if (level == 0 && size == 0) { // the descent is over: open the beam at `cur` (its distance is known; the
                 if (lane == 0) {           // reference measures it again, index.hpp:3436, so the counter advances)
                     top_d()[0] = cur_d, top_i()[0] = cur;
@@ -667,6 +681,7 @@ __global__ void __launch_bounds__(kGroupThreads, 6) group_search_kernel(const __
     w.seq = 0, w.last = p.flag_base, w.dead = false, w.a2 = 0.f, w.cur_q = 0xFFFFFFFFu;
     w.waited = (p.me == p.root);
     w.st_dist = w.st_pops = w.st_hops = w.st_rounds = w.st_rows = 0;
+    w.cy_produce = w.cy_local = w.cy_wait = w.cy_consume = 0;
     w.t0 = globaltimer_ns();
 
     // the root's query staging buffer is complete when its kernel starts (stream order): tell everybody
@@ -699,6 +714,10 @@ __global__ void __launch_bounds__(kGroupThreads, 6) group_search_kernel(const __
         atomicAdd(&p.counters[3], (unsigned long long)w.st_hops);
         atomicAdd(&p.counters[4], (unsigned long long)w.st_rounds);
         atomicAdd(&p.counters[5], (unsigned long long)w.st_rows);
+        if (w.cy_produce | w.cy_wait) {
+            atomicAdd(&p.counters[8], (unsigned long long)w.cy_produce), atomicAdd(&p.counters[9], (unsigned long long)w.cy_local);
+            atomicAdd(&p.counters[10], (unsigned long long)w.cy_wait), atomicAdd(&p.counters[11], (unsigned long long)w.cy_consume);
+        }
         __threadfence();
         last_warp = atomicAdd(&p.counters[0], 1ull) == (unsigned long long)gridDim.x * kGroupWarps - 1ull;
     }
@@ -1017,8 +1036,8 @@ class GroupRank {
         LB_CUDA(cudaMalloc(&d_vis, owned * words_per_slot * 4));
         LB_CUDA(cudaMemset(d_vis, 0, owned * words_per_slot * 4));
         LB_CUDA(cudaMalloc(&d_touched, owned * (size_t)touched_cap * 4));
-        LB_CUDA(cudaMalloc(&d_counters, 8 * sizeof(unsigned long long)));
-        LB_CUDA(cudaMemset(d_counters, 0, 8 * sizeof(unsigned long long)));
+        LB_CUDA(cudaMalloc(&d_counters, 16 * sizeof(unsigned long long)));
+        LB_CUDA(cudaMemset(d_counters, 0, 16 * sizeof(unsigned long long)));
         // staging of raw input queries for the host-buffer entry point: allocated NOW -- a cudaMalloc between the launches of a
         // search may wait for kernels already running on this device, and those kernels wait for the rank that is allocating
         in_bytes = max_batch * std::max<size_t>(row_bytes, cfg.dims * 4);
@@ -1092,7 +1111,7 @@ class GroupRank {
         p.queries = peer_slab[root] + lay.qbuf, p.query_stride = (uint32_t)row_bytes;
         p.vis = d_vis, p.touched = d_touched, p.words_per_slot = words_per_slot, p.touched_cap = touched_cap;
         p.counters = d_counters;
-        LB_CUDA(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned long long), stream));
+        LB_CUDA(cudaMemsetAsync(d_counters, 0, 16 * sizeof(unsigned long long), stream));
         const size_t smem = (size_t)group_warp_layout((uint32_t)row_bytes, group_ring_slots((uint32_t)row_bytes), L, cap).total * kGroupWarps;
         // roles: O owner warps (one query each at a time; enough for every query this rank owns, but leaving a quarter of the
         // resident warps to the helpers), H helper warps sharing the (G-1) * O inbound mailboxes
@@ -1377,13 +1396,14 @@ void group_stats(Group& G, int which, GroupStats& out) {
     LB_CUDA(cudaSetDevice(r->device));
     LB_CUDA(cudaDeviceSynchronize());
     r->check_error();
-    unsigned long long c[8] = {0};
+    unsigned long long c[16] = {0};
     LB_CUDA(cudaMemcpy(c, r->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
     memset(&out, 0, sizeof(out));
     out.rank = r->rank, out.world = r->world;
     out.queries = r->last_nq;
     out.owner_computed_distances = c[1], out.owner_base_pops = c[2], out.owner_upper_hops = c[3], out.owner_rounds = c[4];
     out.local_rows_evaluated = c[5];
+    out.owner_cycles_produce = c[8], out.owner_cycles_local = c[9], out.owner_cycles_wait = c[10], out.owner_cycles_consume = c[11];
     out.local_row_bytes = c[5] * r->vec_bytes;
     out.rows_held = r->bounds[r->rank + 1] - r->bounds[r->rank];
     float ms = 0.f;
@@ -1479,7 +1499,7 @@ void launch_warp_search(Index& idx, const uint8_t* qbuf, size_t qrow, size_t nq,
         LB_CUDA(cudaMalloc(&idx.d_warp_aux_, idx.warp_aux_bytes_));
     }
     uint8_t* aux = idx.d_warp_aux_;
-    LB_CUDA(cudaMemsetAsync(aux, 0, 256, stream)); // [0,64) counters, [64,72) done, [72,80) qready, [80,84) err
+    LB_CUDA(cudaMemsetAsync(aux, 0, 256, stream)); // [0,128) counters, [128,136) done, [136,144) qready, [144,148) err
     GroupLaunch p;
     memset(&p, 0, sizeof(p));
     p.G = 1, p.me = 0, p.W = W, p.cap = cap, p.ring_slots = group_ring_slots((uint32_t)idx.row_bytes_);
@@ -1493,7 +1513,7 @@ void launch_warp_search(Index& idx, const uint8_t* qbuf, size_t qrow, size_t nq,
     p.res_keys[0] = d_keys, p.res_dists[0] = d_dists;
     p.res_counts[0] = d_counts ? d_counts : (uint32_t*)(aux + 256);
     p.counters = (unsigned long long*)aux;
-    p.done[0] = (unsigned long long*)(aux + 64), p.qready[0] = (unsigned long long*)(aux + 72), p.err[0] = (uint32_t*)(aux + 80);
+    p.done[0] = (unsigned long long*)(aux + 128), p.qready[0] = (unsigned long long*)(aux + 136), p.err[0] = (uint32_t*)(aux + 144);
     p.queries = qbuf, p.query_stride = (uint32_t)qrow;
     p.vis = idx.scratch_.visited, p.touched = idx.scratch_.touched;
     p.words_per_slot = idx.scratch_.words_per_cta, p.touched_cap = idx.scratch_.touched_cap;

@@ -37,7 +37,8 @@ struct GroupLaunch {
     uint32_t* touched; // [O][touched_cap]
     size_t words_per_slot;
     uint32_t touched_cap;
-    unsigned long long* counters; // [0] warps finished, [1] owner dist evals, [2] pops, [3] hops, [4] rounds, [5] local rows evaluated
+    unsigned long long* counters; // [0] warps finished, [1] owner dist evals, [2] pops, [3] hops, [4] rounds, [5] local rows evaluated,
+                                  // [6] next owned query, [7] limbo overflows, [8..11] owner cycles: produce, local, wait, consume
 };
 
 struct GroupStats {
@@ -46,6 +47,7 @@ struct GroupStats {
     uint64_t owner_computed_distances, owner_base_pops, owner_upper_hops, owner_rounds; // of the queries this rank owns
     uint64_t local_rows_evaluated, local_row_bytes;                                       // rows of this rank's slice read
     uint64_t rows_held;
+    uint64_t owner_cycles_produce, owner_cycles_local, owner_cycles_wait, owner_cycles_consume; // SM cycles, summed over owner warps
     double kernel_ms;
 };
 

@@ -39,8 +39,6 @@ def _index(eng, metric, quant, d, n, M=16, efc=64, ef=48, seed=3):
 @pytest.mark.parametrize("ranks", [1, 2, 4, 8])
 @pytest.mark.parametrize("metric,quant,d", [("cos", "f32", 96), ("l2sq", "f32", 768), ("hamming", "b1", 512), ("l2sq", "f16", 72)])
 def test_group_equals_one_gpu(eng, ranks, metric, quant, d):
-    if ranks > 2 and d == 768:
-        pytest.skip("one wide-row case per rank count is enough")
     ndev = eng.device_count()
     devices = [r % ndev for r in range(ranks)]  # several ranks per device when the box has fewer GPUs
     g, X, Q = _index(eng, metric, quant, d, 6000 if d < 768 else 3000)
