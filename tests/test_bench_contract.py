@@ -34,3 +34,24 @@ def test_workload_table():
     assert X.shape == (1000, 16) and abs(float(X.mean())) < 0.2
     b = bench.bits_np(100, 64, 1)
     assert b.shape == (100, 8) and b.dtype.name == "uint8"
+
+
+def test_parity_block_is_tie_aware_and_usable_cores_is_sane():
+    """The same-graph parity block of the bench line: position-wise identity, and the tie-aware row test that lets ids swap
+    inside groups of equal distances (hamming) but nowhere else."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    d = np.array([[1.0, 2.0, 2.0, 3.0], [0.5, 0.6, 0.7, 0.8]], np.float32)
+    k = np.array([[10, 11, 12, 13], [20, 21, 22, 23]], np.uint64)
+    same = bench.parity_block(k, d, k.copy(), d.copy())
+    assert same["identical_id_rows"] == 1.0 and same["rows_identical_up_to_distance_ties"] == 1.0 and same["max_rel_dist_err"] == 0.0
+    swapped = k.copy()
+    swapped[0, 1], swapped[0, 2] = 12, 11  # inside the tie group of row 0
+    p = bench.parity_block(k, d, swapped, d.copy())
+    assert p["identical_id_rows"] == 0.5 and p["rows_identical_up_to_distance_ties"] == 1.0
+    wrong = k.copy()
+    wrong[1, 0], wrong[1, 1] = 21, 20  # distinct distances: a real difference
+    p = bench.parity_block(k, d, wrong, d.copy())
+    assert p["rows_identical_up_to_distance_ties"] == 0.5
+    assert 1 <= bench.usable_cores() <= (os.cpu_count() or 1)
