@@ -98,7 +98,11 @@ __host__ __device__ inline GroupWarpLayout group_warp_layout(uint32_t row_bytes,
 // rows in flight per warp: 2 for 3 KB rows, more for narrow rows (about 6 KB of staging per warp)
 inline uint32_t group_ring_slots(uint32_t row_bytes) {
     uint32_t r = 6144u / row_bytes;
-    return r < 2 ? 2 : (r > 8 ? 8 : r);
+    r = r < 2 ? 2 : (r > 8 ? 8 : r);
+    if (const char* e = getenv("LB200_GROUP_RING_SLOTS")) // experiments: deeper rings cost resident warps
+        if (atoi(e) >= 1 && atoi(e) <= 8)
+            r = (uint32_t)atoi(e);
+    return r;
 }
 
 // ---- one warp = one query slot -------------------------------------------------------------------------------------

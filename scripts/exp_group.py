@@ -65,4 +65,10 @@ for rk in sorted(set([1, ranks])):
           "bit-equal dists %s  rows/query per rank %s  rounds/q %.1f" % (
               rk, ndev, kms, B / kms * 1e3, wall * 1e3, same, np.array_equal(dg.view(np.uint32), d1.view(np.uint32)),
               [round(s["local_rows_evaluated"] / B) for s in sts], sum(s["owner_rounds"] for s in sts) / B), flush=True)
+    for s in sts:  # owner phases per round, microseconds at 1.965 GHz; own rows per round -> microseconds per row
+        rounds = max(1, s["owner_rounds"])
+        us = [s["owner_cycles_" + ph] / rounds / 1965.0 for ph in ("produce", "local", "wait", "consume")]
+        own_rows = (s["owner_computed_distances"] / max(1, rk)) / rounds
+        print("   rank %d: produce %.2f  local rows %.2f  wait %.2f  insert %.2f us/round;  ~%.2f us per own row" % (
+            s["rank"], us[0], us[1], us[2], us[3], us[1] / max(own_rows, 1e-9)), flush=True)
     grp.close()
