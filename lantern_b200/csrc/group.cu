@@ -220,9 +220,11 @@ template <int DM, int SK, int NQ> struct GroupWarp {
         // The ring keeps R rows in flight; the rows behind them are already on their way to L2 (one prefetch per 128-byte line,
         // kPrefetchRows rows ahead), so a slot's refill is an L2 hit instead of a DRAM round trip.  With G GPUs a warp's share of
         // an expansion is a handful of rows: all of them are requested from DRAM at once.
-        constexpr uint32_t kPrefetchRows = 8;
+        // Only for SHORT lists (the latency-bound regime of 4+ GPUs): with 24-48 rows per list (1-2 GPUs) the kernel is
+        // HBM-bound and 8 rows x 3 KB x 3500 warps of prefetch would not fit in L2 -- measured: 20.9 instead of 15.9 ms at G = 1.
+        constexpr uint32_t kPrefetchRows = 8, kPrefetchMaxList = 16;
         const uint32_t pf_off = (uint32_t)lane * 128u;
-        const bool pf_lane = pf_off < p.g.row_bytes;
+        const bool pf_lane = pf_off < p.g.row_bytes && n <= kPrefetchMaxList;
         const uint8_t* base = p.g.vectors - (size_t)p.bounds[p.me] * p.g.row_bytes;
         for (uint32_t t = R; t < min(n, R + kPrefetchRows); ++t)
             if (pf_lane)
