@@ -308,6 +308,11 @@ LB200_EXPORT void lb200_group_search_batch_device(lb200_group_t, void const* d_q
 /* Host-only check of a bootstrap collective (no device needed): every rank sends a rank-stamped blob through `allgather` the
  * way group creation does and verifies what comes back.  Returns 0 when the callback behaves, a non-zero code otherwise. */
 LB200_EXPORT int lb200_group_selftest_exchange(int rank, int world, lb200_allgather_fn allgather, void* allgather_ctx);
+/* Host-only: how a search of `nq` queries splits the `resident_warps` of each of `world` GPUs into owner warps (one query each)
+ * and helper warps (which share the (world-1) * owners inbound mailboxes, at most 32 per helper).  Returns 0 and fills
+ * owners / helpers, or 1 when the warps cannot cover the mailboxes.  Every rank computes the same plan. */
+LB200_EXPORT int lb200_group_plan(int world, size_t nq, uint32_t resident_warps, uint32_t owner_slots_max, uint32_t* owners,
+                                  uint32_t* helpers);
 /* local_rank: 0 for a multi-process group; 0..n_devices-1 for a single-process one.  Synchronises that device. */
 LB200_EXPORT void lb200_group_last_stats(lb200_group_t, int local_rank, lb200_group_stats_t* stats, lb200_error_t* error);
 

@@ -142,6 +142,7 @@ SIGNATURES = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, ERRP]),
     "lb200_group_search_batch_device": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, ERRP]),
+    "lb200_group_plan": (C.c_int, [C.c_int, C.c_size_t, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "lb200_group_selftest_exchange": (C.c_int, [C.c_int, C.c_int, ALLGATHER_FN, C.c_void_p]),
     "lb200_group_last_stats": (None, [C.c_void_p, C.c_int, C.POINTER(GroupStats), ERRP]),
     "lb200_device_count": (C.c_int, []),
@@ -333,6 +334,13 @@ class Group:
             assert len(out) == nbytes * world, (len(out), nbytes, world)
             C.memmove(recv, out, len(out))
         return ALLGATHER_FN(_ag)
+
+    @staticmethod
+    def plan(world, nq, resident_warps, owner_slots_max):
+        """(ok, owners, helpers) of a launch (host-only)."""
+        o, h = C.c_uint32(), C.c_uint32()
+        rc = lib().lb200_group_plan(world, nq, resident_warps, owner_slots_max, C.byref(o), C.byref(h))
+        return rc == 0, o.value, h.value
 
     @staticmethod
     def selftest_exchange(rank, world, allgather):

@@ -685,6 +685,16 @@ LB200_EXPORT void lb200_group_search_batch_device(lb200_group_t h, void const* d
                             (cudaStream_t)cuda_stream);
     });
 }
+LB200_EXPORT int lb200_group_plan(int world, size_t nq, uint32_t resident_warps, uint32_t owner_slots_max, uint32_t* owners,
+                                  uint32_t* helpers) {
+    if (world < 1 || world > 8 || !owners || !helpers)
+        return 1;
+    uint32_t O = 0, H = 0;
+    const bool ok = group_plan(world, nq, resident_warps, owner_slots_max, O, H);
+    *owners = O, *helpers = H;
+    return ok ? 0 : 1;
+}
+
 LB200_EXPORT int lb200_group_selftest_exchange(int rank, int world, lb200_allgather_fn allgather, void* ctx) {
     if (world < 1 || world > 8 || rank < 0 || rank >= world || !allgather)
         return 1;

@@ -798,6 +798,26 @@ __global__ void group_copy_results_kernel(const uint64_t* __restrict__ rk, const
 // host side
 // =====================================================================================================================
 
+// Roles of a launch: O owner warps (one query each at a time; enough for every query this rank owns, but leaving a quarter of
+// the resident warps to the helpers) and H helper warps that share the (G-1) * O inbound mailboxes -- no more helpers than
+// mailboxes, and no helper watches more than 32 (one per lane).  Deterministic in (world, nq, W, Omax): every rank computes
+// the same plan.  Returns false when the resident warps cannot cover the mailboxes.
+bool group_plan(int world, size_t nq, uint32_t W, uint32_t Omax, uint32_t& O, uint32_t& H) {
+    O = (uint32_t)round_up((nq + world - 1) / world, kGroupWarps), H = 0;
+    O = std::min(O, Omax);
+    if (world > 1) {
+        O = std::min<uint32_t>(O, (W - W / 4) & ~3u);
+        if (O == 0)
+            return false;
+        const uint32_t M = (uint32_t)(world - 1) * O;
+        H = std::min<uint32_t>(W - O, (uint32_t)round_up(M, kGroupWarps));
+        H = std::max<uint32_t>(H, (uint32_t)round_up((M + 31) / 32, kGroupWarps));
+        return O + H <= W;
+    }
+    O = std::min(O, W & ~3u);
+    return O > 0;
+}
+
 // every spin in the kernel gives up after this long (LB200_GROUP_TIMEOUT_S, default 20 s; raise it under compute-sanitizer)
 static unsigned long long group_timeout_ns() {
     double sec = 20.0;
@@ -1119,20 +1139,9 @@ class GroupRank {
         p.counters = d_counters;
         LB_CUDA(cudaMemsetAsync(d_counters, 0, 16 * sizeof(unsigned long long), stream));
         const size_t smem = (size_t)group_warp_layout((uint32_t)row_bytes, group_ring_slots((uint32_t)row_bytes), L, cap).total * kGroupWarps;
-        // roles: O owner warps (one query each at a time; enough for every query this rank owns, but leaving a quarter of the
-        // resident warps to the helpers), H helper warps sharing the (G-1) * O inbound mailboxes
-        uint32_t O = (uint32_t)round_up((nq + world - 1) / world, kGroupWarps), H = 0;
-        O = std::min(O, Omax);
-        if (world > 1) {
-            O = std::min<uint32_t>(O, (W - W / 4) & ~3u);
-            const uint32_t M = (uint32_t)(world - 1) * O;
-            H = std::min<uint32_t>(W - O, (uint32_t)round_up(M, kGroupWarps)); // no more helpers than mailboxes
-            H = std::max<uint32_t>(H, (uint32_t)round_up((M + 31) / 32, kGroupWarps)); // a helper watches at most 32
-            if (O + H > W)
-                throw CudaError("group: not enough resident warps for this batch's mailboxes");
-        } else {
-            O = std::min(O, W & ~3u);
-        }
+        uint32_t O = 0, H = 0;
+        if (!group_plan(world, nq, W, Omax, O, H))
+            throw CudaError("group: not enough resident warps for this batch's mailboxes");
         p.O = O, p.H = H, p.W = W;
         const uint32_t grid = (O + H) / kGroupWarps;
         const int nqc = pick_nq((uint32_t)row_bytes);

@@ -52,6 +52,7 @@ struct GroupStats {
 };
 
 struct Group;
+bool group_plan(int world, size_t nq, uint32_t W, uint32_t Omax, uint32_t& O, uint32_t& H);
 Group* group_create_ipc(int rank, int world, lb200_allgather_fn ag, void* ctx);
 Group* group_create_local(const int* devices, int ndev);
 void group_free(Group* G);

@@ -169,6 +169,33 @@ def test_group_bootstrap_two_ranks_gloo(tmp_path):
         assert p.returncode == 0, o
 
 
+def test_group_plan_invariants():
+    """Host logic of the multi-GPU search: how the resident warps of a GPU are split into owners and helpers.  Invariants: whole
+    CTAs; owners + helpers fit; every query a rank owns gets an owner slot when the warps allow it; no more helpers than
+    mailboxes and at most 32 mailboxes per helper; one GPU needs no helpers."""
+    from lantern_b200 import api
+    for world in (1, 2, 3, 4, 8):
+        for nq in (1, 3, 61, 300, 1024, 4096, 5000, 20000):
+            for W in (16 * world, 592, 2368, 3552, 4144):
+                W -= W % (4 * world)
+                omax = min(W, -(-(-(-max(nq, 1) // world)) // 4) * 4)
+                ok, O, H = api.Group.plan(world, nq, W, omax)
+                if not ok:
+                    assert world > 1 and (world - 1) * O > 32 * (W - O)
+                    continue
+                assert O % 4 == 0 and H % 4 == 0 and 0 < O and O + H <= W
+                owned = -(-nq // world)
+                if world == 1:
+                    assert H == 0 and O == min(-(-nq // 4) * 4, W)
+                else:
+                    M = (world - 1) * O
+                    assert O == min(-(-owned // 4) * 4, omax, (W - W // 4) & ~3)
+                    assert 0 < H <= max(-(-M // 4) * 4, 4) and M <= 32 * H
+    # the metric's configuration: 4096 queries, 8 GPUs, 3552 resident warps -> every owned query has its owner, 3040 helpers
+    assert api.Group.plan(8, 4096, 3552, 512) == (True, 512, 3040)
+    assert api.Group.plan(2, 4096, 3552, 2048) == (True, 2048, 1504)
+
+
 REF_HEADER_DIR = "/root/reference/lantern_hnsw/third_party/usearch/c"
 
 
