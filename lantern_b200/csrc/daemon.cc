@@ -89,6 +89,7 @@ struct Request {
 
 struct Daemon {
     lb200_index_t idx = nullptr;
+    lb200_group_t group = nullptr; // --devices: the index is served by a row-sharded group of GPUs (lb200_group_*)
     lb200_scalar_kind_t in_kind = lb200_scalar_f32_k;
     size_t qbytes = 0;
     size_t max_batch = 1024;
@@ -132,7 +133,12 @@ struct Daemon {
             for (size_t i = 0; i < n; ++i)
                 memcpy(qbuf.data() + i * qbytes, batch[i]->query.data(), qbytes);
             lb200_error_t err = nullptr;
-            lb200_search_batch(idx, qbuf.data(), n, qbytes, in_kind, want, batch[0]->ef, keys.data(), dists.data(), counts.data(), &err);
+            if (group)
+                lb200_group_search_batch(group, qbuf.data(), n, qbytes, in_kind, want, batch[0]->ef, keys.data(), dists.data(),
+                                         counts.data(), &err);
+            else
+                lb200_search_batch(idx, qbuf.data(), n, qbytes, in_kind, want, batch[0]->ef, keys.data(), dists.data(),
+                                   counts.data(), &err);
             n_batches++;
             uint64_t prev = max_seen.load();
             while (n > prev && !max_seen.compare_exchange_weak(prev, n)) {
@@ -252,7 +258,7 @@ int parse_quant(const std::string& s) {
 } // namespace
 
 int main(int argc, char** argv) {
-    std::string index_path, sock_path, metric = "l2sq", quant = "f32";
+    std::string index_path, sock_path, metric = "l2sq", quant = "f32", devices;
     int port = 0;
     size_t dims = 0, m = 16, efc = 128, ef = 64;
     Daemon d;
@@ -281,10 +287,12 @@ int main(int argc, char** argv) {
             d.max_batch = (size_t)atol(next());
         else if (a == "--window-us")
             d.window_us = atoi(next());
+        else if (a == "--devices") // e.g. 0,1,2,3,4,5,6,7: serve the index from a row-sharded group of these GPUs
+            devices = next();
         else {
             fprintf(stderr,
                     "usage: %s --index FILE --dim D [--metric l2sq|cos|hamming] [--quant f32|f16|i8|b1] [--m M] [--ef EF]\n"
-                    "          (--socket PATH | --port P) [--max-batch N] [--window-us U]\n",
+                    "          (--socket PATH | --port P) [--max-batch N] [--window-us U] [--devices 0,1,...]\n",
                     argv[0]);
             return 2;
         }
@@ -313,6 +321,26 @@ int main(int argc, char** argv) {
     }
     d.in_kind = o.quantization == lb200_scalar_b1_k ? lb200_scalar_b1_k : lb200_scalar_f32_k;
     d.qbytes = d.in_kind == lb200_scalar_b1_k ? (dims + 7) / 8 : dims * 4;
+    if (!devices.empty()) {
+        // one graph over several GPUs: rows sharded by range, distances evaluated on the owning GPU, results identical to the
+        // single-GPU search (csrc/group.cu).  The loaded index is only the source of the distribution.
+        std::vector<int> devs;
+        for (size_t at = 0; at < devices.size();) {
+            devs.push_back(atoi(devices.c_str() + at));
+            const size_t comma = devices.find(',', at);
+            if (comma == std::string::npos)
+                break;
+            at = comma + 1;
+        }
+        d.group = lb200_group_create_local(devs.data(), (int)devs.size(), &err);
+        if (!err) // streaming scans ask for up to 1000 rows per query (scan.c:249-252)
+            lb200_group_distribute(d.group, d.idx, 0, d.max_batch, d.max_batch * 1000, &err);
+        if (err) {
+            fprintf(stderr, "lb200_group: %s\n", err);
+            return 1;
+        }
+        fprintf(stderr, "lb200_search_daemon: serving from %zu GPUs (row-sharded group)\n", devs.size());
+    }
 
     int ls;
     if (!sock_path.empty()) {

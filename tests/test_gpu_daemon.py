@@ -38,7 +38,10 @@ def ask(s, vec, k, ef=0, cont=False):
     return keys, dists
 
 
-def test_many_backends_are_batched(eng, tmp_path):
+@pytest.mark.parametrize("devices", [None, "group"])
+def test_many_backends_are_batched(eng, tmp_path, devices):
+    """devices = "group": the daemon serves the index from a row-sharded multi-GPU group (--devices; two ranks, on two GPUs when
+    the box has them, else both on GPU 0): same answers as the direct single-GPU batch call."""
     n, d = 20000, 64
     X = structured(n, d, seed=5)
     g = eng.Index(d, "l2sq", "f32", M=16, efc=64, ef=48)
@@ -49,9 +52,11 @@ def test_many_backends_are_batched(eng, tmp_path):
     g.save(path)
     sock = str(tmp_path / "lb200.sock")
     p = subprocess.Popen([DAEMON, "--index", path, "--dim", str(d), "--m", "16", "--ef-construction", "64", "--ef", "48",
-                          "--socket", sock, "--window-us", "2000"], stderr=subprocess.DEVNULL)
+                          "--socket", sock, "--window-us", "2000"] +
+                         (["--devices", "0,1" if eng.device_count() > 1 else "0,0", "--max-batch", "256"] if devices else []),
+                         stderr=subprocess.DEVNULL)
     try:
-        for _ in range(200):
+        for _ in range(600):
             if os.path.exists(sock):
                 break
             time.sleep(0.05)
